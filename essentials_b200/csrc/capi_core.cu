@@ -1,0 +1,164 @@
+/**
+ * @file capi_core.cu
+ * @brief C ABI: errors, contexts, graph handles, transpose, random stream, frontier conversions.
+ */
+#include "capi_common.hxx"
+#include <gunrock/algorithms/generate/random.hxx>
+
+namespace ess {
+std::string& last_error() {
+  static thread_local std::string message;
+  return message;
+}
+int fail(const std::exception& e) {
+  last_error() = e.what();
+  return 999;
+}
+int fail(const char* message, int code) {
+  last_error() = message;
+  return code;
+}
+}  // namespace ess
+
+using namespace gunrock;
+
+extern "C" {
+
+const char* ess_last_error(void) { return ess::last_error().c_str(); }
+int ess_version(void) { return 100; }
+
+int ess_context_create(int device, void* stream, int own_stream, ess_context_t* out) {
+  ESS_TRY
+  if (!out) return ess::fail("ess_context_create: out is null");
+  int count = 0;
+  error::throw_if_exception(cudaGetDeviceCount(&count), "no CUDA device");
+  error::throw_if_exception(device < 0 || device >= count, "ess_context_create: bad device ordinal");
+  auto* h = new ess_context_s;
+  if (own_stream)
+    h->ctx = std::make_shared<gcuda::multi_context_t>(device);
+  else
+    h->ctx = std::make_shared<gcuda::multi_context_t>(device, static_cast<cudaStream_t>(stream));
+  h->single()->scratch();
+  *out = h;
+  return 0;
+  ESS_CATCH
+}
+
+int ess_context_destroy(ess_context_t ctx) {
+  delete ctx;
+  return 0;
+}
+
+int ess_context_synchronize(ess_context_t ctx) {
+  ESS_TRY
+  ctx->single()->synchronize();
+  return 0;
+  ESS_CATCH
+}
+
+int ess_graph_create(int64_t n, int64_t m, int offset_bits, const void* d_row_offsets,
+                     const int32_t* d_column_indices, const float* d_values, int symmetric,
+                     const void* d_column_offsets, const int32_t* d_row_indices, const float* d_csc_values,
+                     ess_graph_t* out) {
+  ESS_TRY
+  if (!out || !d_row_offsets || (m > 0 && !d_column_indices)) return ess::fail("ess_graph_create: null argument");
+  if (offset_bits != 32 && offset_bits != 64) return ess::fail("ess_graph_create: offset_bits must be 32 or 64");
+  if (n < 0 || n > 2147483647LL) return ess::fail("ess_graph_create: vertex ids are int32");
+  if (offset_bits == 32 && m > 2147483647LL) return ess::fail("ess_graph_create: m needs 64-bit offsets");
+  auto* h = new ess_graph_s;
+  h->offset_bits = offset_bits;
+  h->n = n;
+  h->m = m;
+  const void* t_off = d_column_offsets;
+  const int32_t* t_idx = d_row_indices;
+  const float* t_val = d_csc_values;
+  if (symmetric) {
+    t_off = d_row_offsets;
+    t_idx = d_column_indices;
+    t_val = d_values;
+  }
+  h->has_csc = t_off != nullptr;
+  auto* J = const_cast<int32_t*>(d_column_indices);
+  auto* X = const_cast<float*>(d_values);
+  auto* I = const_cast<int32_t*>(t_idx);
+  auto* Xt = const_cast<float*>(t_val);
+  if (offset_bits == 64)
+    h->g64 = graph::build::from_csr_and_csc<int32_t, int64_t, float>(
+        int32_t(n), int64_t(m), (int64_t*)d_row_offsets, J, X, (int64_t*)t_off, I, Xt);
+  else
+    h->g32 = graph::build::from_csr_and_csc<int32_t, int32_t, float>(
+        int32_t(n), int32_t(m), (int32_t*)d_row_offsets, J, X, (int32_t*)t_off, I, Xt);
+  *out = h;
+  return 0;
+  ESS_CATCH
+}
+
+int ess_graph_destroy(ess_graph_t g) {
+  delete g;
+  return 0;
+}
+
+int ess_transpose_csr(int64_t n, int64_t m, int offset_bits, const void* d_row_offsets,
+                      const int32_t* d_column_indices, const float* d_values, void* d_out_offsets,
+                      int32_t* d_out_indices, float* d_out_values) {
+  ESS_TRY
+  if (offset_bits == 64)
+    graph::build::detail::transpose_on_device<int32_t, int64_t, float>(
+        int32_t(n), int64_t(m), (const int64_t*)d_row_offsets, d_column_indices, d_values, d_out_indices,
+        (int64_t*)d_out_offsets, d_out_values);
+  else
+    graph::build::detail::transpose_on_device<int32_t, int32_t, float>(
+        int32_t(n), int32_t(m), (const int32_t*)d_row_offsets, d_column_indices, d_values, d_out_indices,
+        (int32_t*)d_out_offsets, d_out_values);
+  return 0;
+  ESS_CATCH
+}
+
+int ess_randoms(ess_context_t ctx, float* d_out, int64_t n, float begin, float end) {
+  ESS_TRY
+  generate::random::uniform_distribution(d_out, std::size_t(n), begin, end, ctx->single()->stream());
+  error::check_last("ess_randoms");
+  ctx->single()->synchronize();
+  return 0;
+  ESS_CATCH
+}
+
+int ess_frontier_to_bitmap(ess_context_t ctx, const int32_t* d_list, int64_t size, int64_t universe,
+                           uint32_t* d_words, int64_t* popcount) {
+  ESS_TRY
+  auto* c = ctx->single();
+  auto stream = c->stream();
+  auto& scratch = c->scratch();
+  const std::size_t words = (std::size_t(universe) + 31) / 32;
+  cudaMemsetAsync(d_words, 0, words * sizeof(uint32_t), stream);
+  if (size)
+    frontier::kernels::scatter_bits_kernel<<<gcuda::persistent_grid(*c, (std::size_t(size) + 255) / 256, 8), 256, 0,
+                                             stream>>>(d_list, std::size_t(size), d_words);
+  scratch.zero(stream);
+  frontier::kernels::popcount_kernel<<<gcuda::persistent_grid(*c, (words + 255) / 256, 8), 256, 0, stream>>>(
+      d_words, words, scratch.d + gcuda::scratch_t::out_count);
+  error::check_last("ess_frontier_to_bitmap");
+  scratch.fetch(stream);
+  if (popcount) *popcount = int64_t(scratch.h[gcuda::scratch_t::out_count]);
+  return 0;
+  ESS_CATCH
+}
+
+int ess_bitmap_to_frontier(ess_context_t ctx, const uint32_t* d_words, int64_t universe, int32_t* d_list,
+                           int64_t* out_count) {
+  ESS_TRY
+  auto* c = ctx->single();
+  auto stream = c->stream();
+  auto& scratch = c->scratch();
+  const std::size_t words = (std::size_t(universe) + 31) / 32;
+  scratch.zero(stream);
+  frontier::kernels::gather_bits_kernel<<<gcuda::persistent_grid(*c, (words + 255) / 256, 8), 256, 0, stream>>>(
+      d_words, words, d_list, scratch.d + gcuda::scratch_t::out_count);
+  error::check_last("ess_bitmap_to_frontier");
+  scratch.fetch(stream);
+  if (out_count) *out_count = int64_t(scratch.h[gcuda::scratch_t::out_count]);
+  return 0;
+  ESS_CATCH
+}
+
+}  // extern "C"

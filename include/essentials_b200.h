@@ -1,0 +1,160 @@
+/*
+ * essentials_b200.h — C ABI of the B200-native frontier operators.
+ *
+ * The reference (jdwapman/essentials, Gunrock 2.x) has no FFI: its boundary is a C++17 header-template API
+ *  that this repository mirrors under include/gunrock/. This header is the plain-C surface a
+ * non-C++ host (ctypes, cgo, JNI ...) binds instead; every entry point names the reference interface it
+ * stands for (paths relative to the reference tree). All pointers named d_* are DEVICE pointers owned by
+ * the caller; nothing here allocates or frees caller memory; no C++ exception crosses the boundary.
+ *
+ * Return value: 0 on success, otherwise a cudaError_t-compatible code (cudaErrorUnknown = 999 for logical
+ * errors); ess_last_error() returns the message of the calling thread's last failure.
+ *
+ * Types are the ones the reference's drivers use (examples/algorithms/bfs/bfs.cu:16-18):
+ * vertex_t = int32, weight_t = float, edge_t = int32 or int64 chosen per graph by `offset_bits`.
+ */
+#ifndef ESSENTIALS_B200_H
+#define ESSENTIALS_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ESS_API __attribute__((visibility("default")))
+#else
+#define ESS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* operators::load_balance_t (include/gunrock/framework/operators/configs.hxx:31-39), same values. */
+enum ess_load_balance {
+  ESS_LB_THREAD_MAPPED = 0,
+  ESS_LB_WARP_MAPPED = 1, /* not supported, as in the reference */
+  ESS_LB_BLOCK_MAPPED = 2,
+  ESS_LB_BUCKETING = 3,
+  ESS_LB_MERGE_PATH = 4,
+  ESS_LB_MERGE_PATH_V2 = 5, /* alias of merge_path */
+  ESS_LB_WORK_STEALING = 6  /* not supported, as in the reference */
+};
+/* operators::advance_direction_t (configs.hxx:48-52). */
+enum ess_direction { ESS_DIR_FORWARD = 0, ESS_DIR_BACKWARD = 1, ESS_DIR_OPTIMIZED = 2 };
+/* operators::filter_algorithm_t (configs.hxx:54-59). */
+enum ess_filter { ESS_FILTER_REMOVE = 0, ESS_FILTER_PREDICATED = 1, ESS_FILTER_COMPACT = 2, ESS_FILTER_BYPASS = 3 };
+
+typedef struct ess_context_s* ess_context_t; /* gcuda::multi_context_t, include/gunrock/cuda/context.hxx:136-206 */
+typedef struct ess_graph_s* ess_graph_t;     /* graph::graph_t view, include/gunrock/graph/graph.hxx:52-317 */
+
+/* What enact() and the enactor counters report for one run. */
+typedef struct ess_run_info {
+  float enact_ms;     /* value returned by gunrock::<alg>::run(): cudaEvent ms around the BSP loop
+                         (include/gunrock/framework/enactor.hxx:246-253) */
+  int32_t iterations; /* enactor_t::iteration at convergence */
+  int32_t pull_steps; /* direction-optimised BFS: levels run bottom-up */
+  int32_t push_steps; /* direction-optimised BFS: levels run top-down */
+  int64_t reserved[4];
+} ess_run_info;
+
+ESS_API const char* ess_last_error(void);
+ESS_API int ess_version(void);
+
+/* gcuda::multi_context_t(device[, stream]) (context.hxx:143-181): one device. own_stream != 0 creates a new
+ * non-blocking stream owned by the context, as the reference's standard_context_t does (context.hxx:82);
+ * otherwise all work is enqueued on `stream` (a cudaStream_t; NULL = the legacy default stream), so it is
+ * ordered with the caller's other work on that stream. */
+ESS_API int ess_context_create(int device, void* stream, int own_stream, ess_context_t* out);
+ESS_API int ess_context_destroy(ess_context_t ctx);
+ESS_API int ess_context_synchronize(ess_context_t ctx);
+
+/* graph::build::from_csr<device, csr[|csc]> (include/gunrock/graph/build.hxx:21-36).
+ * d_row_offsets: (n+1) x int32 or int64 (offset_bits = 32|64); d_column_indices: m x int32;
+ * d_values: m x float or NULL (weight 1). CSC (in-edges), needed for backward / optimized / pull:
+ *   symmetric != 0            -> the CSC view aliases the CSR arrays (undirected graph);
+ *   d_column_offsets != NULL  -> caller-provided transpose (same widths);
+ *   otherwise                 -> no CSC view; calls that need it fail with an error. */
+ESS_API int ess_graph_create(int64_t n, int64_t m, int offset_bits, const void* d_row_offsets,
+                     const int32_t* d_column_indices, const float* d_values, int symmetric,
+                     const void* d_column_offsets, const int32_t* d_row_indices, const float* d_csc_values,
+                     ess_graph_t* out);
+ESS_API int ess_graph_destroy(ess_graph_t g);
+
+/* CSR -> CSC by counting sort on the device (the transpose the reference performs destructively inside
+ * graph/detail/build.hxx:103-110). Output buffers are caller-allocated: (n+1) offsets, m indices, m values
+ * (d_values / d_out_values may both be NULL). Order inside a column is unspecified. */
+ESS_API int ess_transpose_csr(int64_t n, int64_t m, int offset_bits, const void* d_row_offsets,
+                      const int32_t* d_column_indices, const float* d_values, void* d_out_offsets,
+                      int32_t* d_out_indices, float* d_out_values);
+
+/* gunrock::bfs::run(G, source, distances, predecessors, context) — include/gunrock/algorithms/bfs.hxx:151-176.
+ * d_depth: n x int32, INT32_MAX = unreachable. lb: ess_load_balance; direction: FORWARD (reference
+ * behaviour) or OPTIMIZED (push/pull switching; needs a CSC view). alpha/beta <= 0 keep the defaults. */
+ESS_API int ess_bfs(ess_context_t ctx, ess_graph_t g, int32_t source, int32_t* d_depth, int lb, int direction,
+            float alpha, float beta, ess_run_info* info);
+
+/* gunrock::sssp::run — include/gunrock/algorithms/sssp.hxx:155-185. d_dist: n x float, FLT_MAX = unreachable. */
+ESS_API int ess_sssp(ess_context_t ctx, ess_graph_t g, int32_t source, float* d_dist, int lb, ess_run_info* info);
+
+/* gunrock::pr::run — include/gunrock/algorithms/pr.hxx:183-216 (alpha 0.85, tol 1e-6 in examples/algorithms/pr/pr.cu:55-56).
+ * pull != 0 gathers over the CSC view instead of scattering with atomics. */
+ESS_API int ess_pagerank(ess_context_t ctx, ess_graph_t g, float alpha, float tol, int max_iterations, float* d_p, int lb,
+                 int pull, ess_run_info* info);
+
+/* gunrock::ppr::run — include/gunrock/algorithms/ppr.hxx:150-179. d_p: n x float. */
+ESS_API int ess_ppr(ess_context_t ctx, ess_graph_t g, int32_t seed, float alpha, float epsilon, float* d_p, int lb,
+            ess_run_info* info);
+
+/* gunrock::kcore::run — include/gunrock/algorithms/kcore.hxx:202-222. d_k_cores: n x int32. */
+ESS_API int ess_kcore(ess_context_t ctx, ess_graph_t g, int32_t* d_k_cores, int lb, ess_run_info* info);
+
+/* gunrock::color::run — include/gunrock/algorithms/color.hxx:155-180. d_colors: n x int32. */
+ESS_API int ess_color(ess_context_t ctx, ess_graph_t g, int32_t* d_colors, ess_run_info* info);
+
+/* generate::random::uniform_distribution — include/gunrock/algorithms/generate/random.hxx:20-33. */
+ESS_API int ess_randoms(ess_context_t ctx, float* d_out, int64_t n, float begin, float end);
+
+/* ---- operator-level entry points (used by the parity tests; fixed test operators) ---------------------
+ * operators::advance::execute<lb, direction, vertices, vertices>(G, op, in, out, segments, ctx) —
+ * include/gunrock/framework/operators/advance/advance.hxx:91-129 — with the operator
+ *     op(src, nbr, e, w) := { atomicAdd(&d_edge_calls[e], 1); return (src + nbr + e) % modulus != 0; }
+ * d_out receives the kept neighbours (capacity out_capacity elements; 0 lets the library size it and only
+ * report the count), *out_count their number. d_edge_calls (m x int32, caller-zeroed) may be NULL. */
+ESS_API int ess_advance_probe(ess_context_t ctx, ess_graph_t g, int lb, int direction, const int32_t* d_frontier,
+                      int64_t frontier_size, int32_t* d_out, int64_t out_capacity, int64_t* out_count,
+                      int32_t* d_edge_calls, int32_t modulus);
+
+/* operators::filter::execute<alg>(G, op, in, out, ctx) — include/gunrock/framework/operators/filter/filter.hxx:59-86 —
+ * with op(v) := { atomicAdd(&d_calls[v], 1); return v % modulus != 0; }. d_out needs `size` elements
+ * (may equal d_in for BYPASS). */
+ESS_API int ess_filter_probe(ess_context_t ctx, ess_graph_t g, int alg, const int32_t* d_in, int64_t size, int32_t* d_out,
+                     int64_t* out_count, int32_t* d_calls, int32_t modulus);
+
+/* frontier sparse -> dense (bitmap, 1 bit per vertex; d_words: ceil(universe/32)+1 x uint32) and back
+ * (ascending within 1024-vertex groups). Stand for the conversions SURVEY.md K14 R3/R4 lists; the
+ * reference's boolmap_frontier_t (frontier/experimental/boolmap_frontier.hxx:25-202) has none. */
+ESS_API int ess_frontier_to_bitmap(ess_context_t ctx, const int32_t* d_list, int64_t size, int64_t universe,
+                           uint32_t* d_words, int64_t* popcount);
+ESS_API int ess_bitmap_to_frontier(ess_context_t ctx, const uint32_t* d_words, int64_t universe, int32_t* d_list,
+                           int64_t* out_count);
+
+/* ---- multi-GPU (one process per GPU; 1-D vertex partition; exchange done by the host with NCCL) --------
+ * One BFS level on the rows [row_begin, row_begin + local graph n) this rank owns; `g` holds those rows
+ * with GLOBAL column ids (symmetric graph). Bitmaps cover all global vertices.
+ *   pull = 0: expand the owned vertices that are set in d_frontier_bits; every neighbour not in
+ *             d_visited_bits is OR-ed into d_candidate_bits (global length) — the host then exchanges
+ *             candidate slices and calls ess_bfs_absorb on the owner.
+ *   pull = 1: for every owned vertex not in d_visited_bits, look for an in-neighbour in d_frontier_bits;
+ *             found vertices are set in d_candidate_bits (owned slice only, no exchange of candidates needed).
+ * ess_bfs_absorb: for owned vertices, fresh = candidate & ~visited; depth[fresh] = level; visited |= fresh;
+ * writes fresh into d_next_bits (owned slice) and returns |fresh| and Σdeg(fresh). */
+ESS_API int ess_bfs_partition_step(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int64_t n_global, int pull,
+                           const uint32_t* d_frontier_bits, const uint32_t* d_visited_bits,
+                           uint32_t* d_candidate_bits);
+ESS_API int ess_bfs_absorb(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int64_t n_global, int32_t level,
+                   const uint32_t* d_candidate_bits, uint32_t* d_visited_bits, uint32_t* d_next_bits,
+                   int32_t* d_depth_local, int64_t* fresh_vertices, int64_t* fresh_edges);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESSENTIALS_B200_H */

@@ -1,0 +1,110 @@
+/**
+ * @file bfs.hxx
+ * @brief Breadth-first search client of the frontier operators.
+ *
+ * Same problem/enactor/run shape and the same per-edge operator as the reference
+ * (include/gunrock/algorithms/bfs.hxx:80-132: old = atomic::min(&dist[nbr], iter+1); keep iff iter+1 < old;
+ * reset :53-60 fills INT_MAX and zeroes the source). run() keeps the reference signature (:151-159); the
+ * two leading template parameters are additive and select the load balancer and the direction, so
+ *   bfs::run(G, src, dist, pred)                                   == reference behaviour (block_mapped push)
+ *   bfs::run<load_balance_t::merge_path, advance_direction_t::optimized>(...)  = push/pull switching
+ * Depths are an order-independent fixed point, so every variant returns the same array.
+ */
+#pragma once
+
+#include <gunrock/algorithms/algorithms.hxx>
+
+namespace gunrock {
+namespace bfs {
+
+template <typename vertex_t>
+struct param_t {
+  vertex_t single_source;
+  param_t(vertex_t _single_source) : single_source(_single_source) {}
+};
+
+template <typename vertex_t>
+struct result_t {
+  vertex_t* distances;
+  vertex_t* predecessors;  ///< accepted for signature parity; not produced (the reference leaves it a todo)
+  result_t(vertex_t* _distances, vertex_t* _predecessors) : distances(_distances), predecessors(_predecessors) {}
+};
+
+template <typename graph_t, typename param_type, typename result_type>
+struct problem_t : gunrock::problem_t<graph_t> {
+  param_type param;
+  result_type result;
+  using vertex_t = typename graph_t::vertex_type;
+  using edge_t = typename graph_t::edge_type;
+  using weight_t = typename graph_t::weight_type;
+
+  problem_t(graph_t& G, param_type& _param, result_type& _result, std::shared_ptr<gcuda::multi_context_t> _context)
+      : gunrock::problem_t<graph_t>(G, _context), param(_param), result(_result) {}
+
+  void init() override {}
+  void reset() override {
+    auto* ctx = this->get_single_context();
+    const std::size_t n = std::size_t(this->get_graph().get_number_of_vertices());
+    b200::fill(*ctx, result.distances, n, std::numeric_limits<vertex_t>::max());
+    b200::set_one(*ctx, result.distances + param.single_source, vertex_t(0));
+  }
+};
+
+template <typename problem_t, operators::load_balance_t lb, operators::advance_direction_t direction>
+struct enactor_t : gunrock::enactor_t<problem_t> {
+  using base_t = gunrock::enactor_t<problem_t>;
+  using vertex_t = typename problem_t::vertex_t;
+  using edge_t = typename problem_t::edge_t;
+  using weight_t = typename problem_t::weight_t;
+  using frontier_t = typename base_t::frontier_t;
+
+  enactor_t(problem_t* _problem, std::shared_ptr<gcuda::multi_context_t> _context,
+            enactor_properties_t _properties = enactor_properties_t())
+      : base_t(_problem, _context, _properties) {}
+
+  void prepare_frontier(frontier_t* f, gcuda::multi_context_t& context) override {
+    f->push_back(this->get_problem()->param.single_source);
+  }
+
+  void loop(gcuda::multi_context_t& context) override {
+    auto E = this->get_enactor();
+    auto P = this->get_problem();
+    auto G = P->get_graph();
+    auto distances = P->result.distances;
+    const vertex_t next_depth = vertex_t(this->iteration + 1);
+
+    auto search = [distances, next_depth] __host__ __device__(vertex_t const& source, vertex_t const& neighbor,
+                                                              edge_t const& edge, weight_t const& weight) -> bool {
+      return next_depth < math::atomic::min(&distances[neighbor], next_depth);
+    };
+    operators::advance::execute<lb, direction>(G, E, search, context);
+  }
+};
+
+template <operators::load_balance_t lb = operators::load_balance_t::block_mapped,
+          operators::advance_direction_t direction = operators::advance_direction_t::forward, typename graph_t>
+float run(graph_t& G, typename graph_t::vertex_type& single_source, typename graph_t::vertex_type* distances,
+          typename graph_t::vertex_type* predecessors,
+          std::shared_ptr<gcuda::multi_context_t> context =
+              std::shared_ptr<gcuda::multi_context_t>(new gcuda::multi_context_t(0)),
+          enactor_properties_t properties = enactor_properties_t(), int* pull_steps = nullptr, int* iterations = nullptr) {
+  using vertex_t = typename graph_t::vertex_type;
+  using param_type = param_t<vertex_t>;
+  using result_type = result_t<vertex_t>;
+  using problem_type = problem_t<graph_t, param_type, result_type>;
+  using enactor_type = enactor_t<problem_type, lb, direction>;
+
+  param_type param(single_source);
+  result_type result(distances, predecessors);
+  problem_type problem(G, param, result, context);
+  problem.init();
+  problem.reset();
+  enactor_type enactor(&problem, context, properties);
+  float ms = enactor.enact();
+  if (pull_steps) *pull_steps = enactor.direction.pull_steps;
+  if (iterations) *iterations = enactor.iteration;
+  return ms;
+}
+
+}  // namespace bfs
+}  // namespace gunrock

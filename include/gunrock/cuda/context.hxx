@@ -1,0 +1,217 @@
+/**
+ * @file context.hxx
+ * @brief gcuda::standard_context_t (one device: stream, event, timer, properties, operator scratch) and
+ * gcuda::multi_context_t (the vector of per-device contexts every operator takes).
+ *
+ * API kept from the reference (include/gunrock/cuda/context.hxx:54-206): the four multi_context_t
+ * constructors, get_context(i), size(), enable_peer_access(), public `contexts`/`devices`;
+ * standard_context_t::{stream, synchronize, event, timer, props, ptx_version, ordinal, execution_policy}.
+ * Dropped: mgpu() (moderngpu is not used). Added for the B200 operators: scratch() — persistent
+ * per-context device counters + pinned host mirror + a growable temp arena, so no operator call ever
+ * allocates (the reference cudaMallocs inside every block_mapped advance, block_mapped.hxx:200) — and an
+ * optional distributed descriptor (rank / world size) used by the 1-D partitioned multi-GPU enactors.
+ */
+#pragma once
+
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime_api.h>
+#include <thrust/execution_policy.h>
+#include <thrust/system/cuda/execution_policy.h>
+
+#include <gunrock/error.hxx>
+#include <gunrock/memory.hxx>
+#include <gunrock/util/timer.hxx>
+
+namespace gunrock {
+namespace gcuda {
+
+using device_id_t = int;
+using stream_t = cudaStream_t;
+using event_t = cudaEvent_t;
+using device_properties_t = cudaDeviceProp;
+
+struct compute_capability_t {
+  int major, minor;
+  constexpr int as_combined_number() const { return major * 10 + minor; }
+};
+constexpr compute_capability_t make_compute_capability(int combined) {
+  return compute_capability_t{combined / 10, combined % 10};
+}
+
+/**
+ * @brief Operator workspace living next to a stream. Slots of the counter block (device + pinned host
+ * mirror) are named here so kernels and host code agree.
+ */
+struct scratch_t {
+  enum slot : int {
+    out_count = 0,    // elements appended to the output frontier
+    work_total = 1,   // sum of degrees of the input frontier (edges to expand)
+    overflow = 2,     // required capacity when an output buffer was too small (0 = fine)
+    items = 3,        // non-empty work items after preparation
+    ticket = 4,       // dynamic tile ticket for single-pass scans
+    big_count = 5,    // deferred high-degree items
+    aux0 = 6,
+    aux1 = 7,
+    aux2 = 8,
+    aux3 = 9,
+    n_slots = 16
+  };
+
+  unsigned long long* d = nullptr;  // device counters
+  unsigned long long* h = nullptr;  // pinned host mirror
+  memory::device_array_t<unsigned char> arena;
+  std::uint64_t max_degree_key = 0;  // cache: (offsets pointer ^ n) -> max degree
+  long long max_degree_val = -1;
+
+  scratch_t() = default;
+  scratch_t(const scratch_t&) = delete;
+  scratch_t& operator=(const scratch_t&) = delete;
+  ~scratch_t() {
+    if (d) cudaFree(d);
+    if (h) cudaFreeHost(h);
+  }
+  void init() {
+    if (d) return;
+    error::throw_if_exception(cudaMalloc(&d, n_slots * sizeof(unsigned long long)), "scratch counters");
+    error::throw_if_exception(cudaMallocHost(&h, n_slots * sizeof(unsigned long long)), "scratch mirror");
+    error::throw_if_exception(cudaMemset(d, 0, n_slots * sizeof(unsigned long long)), "scratch memset");
+    for (int i = 0; i < n_slots; ++i) h[i] = 0;
+  }
+  /// Temp arena of at least `bytes` (256-byte aligned sub-allocation is the caller's business).
+  unsigned char* temp(std::size_t bytes) {
+    if (arena.capacity() < bytes)
+      arena.reserve(bytes + bytes / 2 + 4096, /*keep=*/false);
+    return arena.data();
+  }
+  void zero(stream_t s) { cudaMemsetAsync(d, 0, n_slots * sizeof(unsigned long long), s); }
+  /// Copies the counter block to the pinned mirror and waits for the stream: one sync per operator.
+  void fetch(stream_t s) {
+    cudaMemcpyAsync(h, d, n_slots * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+    error::throw_if_exception(cudaStreamSynchronize(s), "operator stream sync");
+  }
+};
+
+/// Bump allocator over scratch_t::temp(): lay out all temporaries of one operator call, then carve.
+struct arena_layout_t {
+  std::size_t bytes = 0;
+  std::size_t add(std::size_t n) {
+    std::size_t at = bytes;
+    bytes += (n + 255) & ~std::size_t(255);
+    return at;
+  }
+};
+
+class standard_context_t {
+ public:
+  explicit standard_context_t(device_id_t device = 0) : _ordinal(device), _owns_stream(true) {
+    cudaSetDevice(_ordinal);
+    error::throw_if_exception(cudaStreamCreateWithFlags(&_stream, cudaStreamNonBlocking), "stream create");
+    init();
+  }
+  standard_context_t(cudaStream_t stream, device_id_t device = 0)
+      : _ordinal(device), _stream(stream), _owns_stream(false) {
+    cudaSetDevice(_ordinal);
+    init();
+  }
+  standard_context_t(const standard_context_t&) = delete;
+  standard_context_t& operator=(const standard_context_t&) = delete;
+  ~standard_context_t() {
+    cudaEventDestroy(_event);
+    if (_owns_stream) cudaStreamDestroy(_stream);
+  }
+
+  const device_properties_t& props() const { return _props; }
+  void print_properties();
+  compute_capability_t ptx_version() const { return make_compute_capability(_props.major * 10 + _props.minor); }
+  stream_t stream() { return _stream; }
+  event_t event() { return _event; }
+  util::timer_t& timer() { return _timer; }
+  device_id_t ordinal() const { return _ordinal; }
+  int sm_count() const { return _props.multiProcessorCount; }
+
+  void synchronize() {
+    error::throw_if_exception(_stream ? cudaStreamSynchronize(_stream) : cudaDeviceSynchronize(),
+                              "context synchronize");
+  }
+
+  /// Thrust policy on this stream; kept because algorithm code outside the operators calls Thrust with it.
+  auto execution_policy() { return thrust::cuda::par_nosync.on(_stream); }
+
+  scratch_t& scratch() {
+    _scratch.init();
+    return _scratch;
+  }
+
+ private:
+  void init() {
+    error::throw_if_exception(cudaEventCreateWithFlags(&_event, cudaEventDisableTiming), "event create");
+    error::throw_if_exception(cudaGetDeviceProperties(&_props, _ordinal), "device properties");
+    _timer.set_stream(_stream);
+  }
+
+  device_properties_t _props{};
+  device_id_t _ordinal;
+  stream_t _stream{};
+  bool _owns_stream;
+  event_t _event{};
+  util::timer_t _timer;
+  scratch_t _scratch;
+};
+
+inline void standard_context_t::print_properties() {
+  std::printf("device %d: %s, sm_%d%d, %d SMs, %.1f GB, L2 %.0f MB\n", _ordinal, _props.name, _props.major,
+              _props.minor, _props.multiProcessorCount, _props.totalGlobalMem / 1e9, _props.l2CacheSize / 1e6);
+}
+
+class multi_context_t {
+ public:
+  std::vector<standard_context_t*> contexts;
+  std::vector<device_id_t> devices;
+  static constexpr std::size_t MAX_NUMBER_OF_GPUS = 1024;
+
+  /// 1-D partition descriptor for one-process-per-GPU runs (rank owns a contiguous vertex range).
+  int rank = 0;
+  int world_size = 1;
+
+  template <typename device_list_t, typename = decltype(std::declval<device_list_t>().begin())>
+  explicit multi_context_t(const device_list_t& _devices) : devices(_devices.begin(), _devices.end()) {
+    for (auto dev : devices) contexts.push_back(new standard_context_t(dev));
+  }
+  template <typename device_list_t, typename = decltype(std::declval<device_list_t>().begin())>
+  multi_context_t(const device_list_t& _devices, cudaStream_t _stream) : devices(_devices.begin(), _devices.end()) {
+    for (auto dev : devices) contexts.push_back(new standard_context_t(_stream, dev));
+  }
+  multi_context_t(device_id_t _device) : devices(1, _device) { contexts.push_back(new standard_context_t(_device)); }
+  multi_context_t(device_id_t _device, cudaStream_t _stream) : devices(1, _device) {
+    contexts.push_back(new standard_context_t(_stream, _device));
+  }
+  multi_context_t(const multi_context_t&) = delete;
+  multi_context_t& operator=(const multi_context_t&) = delete;
+  ~multi_context_t() {
+    for (auto* c : contexts) delete c;
+  }
+
+  standard_context_t* get_context(device_id_t device) { return contexts[device]; }
+  std::size_t size() const { return contexts.size(); }
+
+  void enable_peer_access() {
+    int count = int(size());
+    for (int i = 0; i < count; ++i) {
+      cudaSetDevice(contexts[i]->ordinal());
+      for (int j = 0; j < count; ++j) {
+        if (i == j) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, contexts[i]->ordinal(), contexts[j]->ordinal());
+        if (can) {
+          cudaError_t st = cudaDeviceEnablePeerAccess(contexts[j]->ordinal(), 0);
+          if (st == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        }
+      }
+    }
+    if (count) cudaSetDevice(contexts[0]->ordinal());
+  }
+};
+
+}  // namespace gcuda
+}  // namespace gunrock

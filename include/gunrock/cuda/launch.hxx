@@ -1,0 +1,54 @@
+/**
+ * @file launch.hxx
+ * @brief Launch geometry for B200 and the thread-index helpers of the reference's gcuda namespace.
+ *
+ * The reference picks launch parameters at compile time from an SM_TARGET macro through launch_box_t
+ * (include/gunrock/cuda/launch_box.hxx:194-335, sm flags end at sm_86: include/gunrock/cuda/sm.hxx:23-39).
+ * This build targets exactly one architecture (sm_100a, 148 SMs), so the "launch box" collapses to a
+ * persistent-grid rule: operators launch min(needed CTAs, SMs x resident CTAs) and grid-stride.
+ */
+#pragma once
+
+#include <cuda_runtime_api.h>
+#include <gunrock/cuda/context.hxx>
+
+namespace gunrock {
+namespace gcuda {
+
+enum sm_flag_t : unsigned { fallback = ~0u, sm_100 = 1u << 16 };
+
+namespace thread {
+namespace global {
+namespace id {
+__device__ __forceinline__ std::size_t x() { return std::size_t(blockIdx.x) * blockDim.x + threadIdx.x; }
+}  // namespace id
+}  // namespace global
+namespace local {
+namespace id {
+__device__ __forceinline__ unsigned x() { return threadIdx.x; }
+}  // namespace id
+}  // namespace local
+}  // namespace thread
+namespace block {
+namespace id {
+__device__ __forceinline__ unsigned x() { return blockIdx.x; }
+}  // namespace id
+namespace size {
+__device__ __forceinline__ unsigned x() { return blockDim.x; }
+}  // namespace size
+}  // namespace block
+namespace grid {
+namespace size {
+__device__ __forceinline__ unsigned x() { return gridDim.x; }
+}  // namespace size
+}  // namespace grid
+
+/// CTAs for a grid-stride kernel: enough to cover `work_ctas`, capped at SMs x `resident`.
+inline unsigned persistent_grid(standard_context_t& ctx, std::size_t work_ctas, int resident) {
+  std::size_t cap = std::size_t(ctx.sm_count()) * std::size_t(resident);
+  std::size_t g = work_ctas < cap ? work_ctas : cap;
+  return unsigned(g ? g : 1);
+}
+
+}  // namespace gcuda
+}  // namespace gunrock

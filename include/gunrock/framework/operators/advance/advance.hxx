@@ -1,0 +1,345 @@
+/**
+ * @file advance.hxx
+ * @brief operators::advance::execute — neighbour expansion of a frontier.
+ *
+ * Public signatures are the reference's (include/gunrock/framework/operators/advance/advance.hxx:91-104
+ * explicit buffers, :192-221 enactor form, default template arguments included):
+ *
+ *   advance::execute<lb, direction, input_type, output_type>(G, E, op, context, swap_buffers = true)
+ *   advance::execute<lb, direction, input_type, output_type>(G, op, input*, output*, segments, context)
+ *
+ * op is  bool(vertex_t const& src, vertex_t const& nbr, edge_t const& e, weight_t const& w)  invoked with
+ * lvalues exactly once per (frontier item, edge). Behavioural contract vs the reference:
+ *   - output holds the neighbours for which op returned true. The reference writes one slot per edge and
+ *     marks failures with -1 (block_mapped.hxx:143-144); here survivors are compacted, so
+ *     get_number_of_elements() is the number of survivors. Slot order is unspecified in both.
+ *   - direction::backward walks the CSC view for every balancer (the reference honours it only in
+ *     merge_path, merge_path.hxx:59-61).
+ *   - direction::optimized (reference: throws, merge_path.hxx:41-43) switches between push over CSR and pull
+ *     over CSC with a visited bitmap kept in E->direction; see pull.cuh for its operator contract. Only the
+ *     enactor form supports it, and the graph must hold both views.
+ *   - load_balance_t::bucketing (reference: empty body, bucketing.hxx:31-36, never dispatched) is implemented.
+ *   - warp_mapped / work_stealing / edge frontiers throw "not supported", as the reference does.
+ *   - more than one context in `context` throws like the reference (advance.hxx:125-128): multi-GPU runs
+ *     are one process per GPU, each with a single-device context (DESIGN.md "multi-GPU").
+ * Host cost per call: one counter memset, 1-4 kernel launches, one 128-byte D2H and ONE stream
+ * synchronisation (the reference: >=3 syncs + cudaMalloc/cudaFree).
+ */
+#pragma once
+
+#include <gunrock/cuda/cuda.hxx>
+#include <gunrock/error.hxx>
+#include <gunrock/util/type_limits.hxx>
+#include <gunrock/framework/operators/configs.hxx>
+#include <gunrock/framework/operators/advance/kernels.cuh>
+#include <gunrock/framework/operators/advance/pull.cuh>
+
+namespace gunrock {
+namespace operators {
+namespace advance {
+
+namespace detail {
+
+using gcuda::scratch_t;
+using kernels::counter_t;
+using kernels::visit_t;
+
+/// Max degree of the adjacency, computed once per (context, offsets array) and cached.
+template <typename vertex_t, typename edge_t>
+long long max_degree(gcuda::standard_context_t& ctx, const edge_t* offsets, vertex_t n) {
+  auto& s = ctx.scratch();
+  const std::uint64_t key = std::uint64_t(reinterpret_cast<std::uintptr_t>(offsets)) ^ (std::uint64_t(n) << 1) ^ 1u;
+  if (s.max_degree_key == key && s.max_degree_val >= 0) return s.max_degree_val;
+  auto stream = ctx.stream();
+  cudaMemsetAsync(s.d + scratch_t::aux3, 0, sizeof(counter_t), stream);
+  kernels::max_degree_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 8), 256, 0, stream>>>(
+      offsets, n, s.d + scratch_t::aux3);
+  s.fetch(stream);
+  s.max_degree_key = key;
+  s.max_degree_val = (long long)s.h[scratch_t::aux3];
+  return s.max_degree_val;
+}
+
+/// Raw device pointer of a work-offsets container (our device_array_t or a thrust::device_vector).
+template <typename pointer_t>
+auto raw_of(pointer_t p) {
+  if constexpr (std::is_pointer<pointer_t>::value)
+    return p;
+  else
+    return p.get();
+}
+
+template <typename frontier_t>
+void grow_output(frontier_t* output, std::size_t needed) {
+  if (output->get_capacity() < needed) output->reserve(needed);
+}
+
+/**
+ * @brief Push-direction expansion with one of the balancers. `visited` non-null selects the
+ * test-and-set policy (direction-optimised callers); null keeps reference semantics.
+ * `input_size_on_device`/`next_edges` are used by the optimised path only.
+ */
+template <load_balance_t lb, bool use_csc, advance_io_type_t input_type, advance_io_type_t output_type, visit_t policy,
+          typename graph_t, typename operator_t, typename frontier_t, typename work_tiles_t>
+void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, work_tiles_t& segments,
+            gcuda::standard_context_t& ctx, unsigned* visited) {
+  using vertex_t = typename graph_t::vertex_type;
+  using edge_t = typename graph_t::edge_type;
+  constexpr bool graph_input = input_type == advance_io_type_t::graph;
+  constexpr bool has_output = output_type != advance_io_type_t::none;
+  static_assert(input_type == advance_io_type_t::graph || input_type == advance_io_type_t::vertices,
+                "advance input must be `graph` or `vertices`");
+  static_assert(output_type == advance_io_type_t::none || output_type == advance_io_type_t::vertices,
+                "advance output must be `vertices` or `none`");
+
+  const auto A = graph::adjacency_of<use_csc>(G);
+  const std::size_t nf = graph_input ? std::size_t(A.n) : input->get_number_of_elements();
+  if (nf == 0) {
+    if constexpr (has_output) output->set_number_of_elements(0);
+    return;
+  }
+  auto& scratch = ctx.scratch();
+  auto stream = ctx.stream();
+  const vertex_t* in = graph_input ? nullptr : input->data();
+  const std::size_t prep_tiles = (nf + kernels::cta_threads * kernels::prep_items - 1) /
+                                 (kernels::cta_threads * kernels::prep_items);
+  const std::size_t item_ctas = (nf + kernels::cta_threads - 1) / kernels::cta_threads;
+
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    scratch.zero(stream);
+    vertex_t* out = has_output ? output->data() : nullptr;
+    const counter_t capacity = has_output ? counter_t(output->get_capacity()) : counter_t(0);
+    counter_t* C = scratch.d;
+
+    if constexpr (lb == load_balance_t::thread_mapped || lb == load_balance_t::block_mapped) {
+      const long long maxdeg = max_degree(ctx, A.offsets, A.n);
+      const bool guard = has_output && (long double)(nf) * (long double)(maxdeg) > (long double)(capacity);
+      if (guard)
+        kernels::degree_sum_kernel<graph_input><<<gcuda::persistent_grid(ctx, item_ctas, 8), 256, 0, stream>>>(
+            A.offsets, in, nf, C);
+      if constexpr (lb == load_balance_t::thread_mapped) {
+        const unsigned grid = gcuda::persistent_grid(ctx, item_ctas, 8);
+        if (guard)
+          kernels::thread_mapped_kernel<graph_input, has_output, true, policy>
+              <<<grid, 256, 0, stream>>>(A, op, in, nf, nullptr, out, C, capacity, visited);
+        else
+          kernels::thread_mapped_kernel<graph_input, has_output, false, policy>
+              <<<grid, 256, 0, stream>>>(A, op, in, nf, nullptr, out, C, capacity, visited);
+      } else {
+        vertex_t* big_list = nullptr;
+        if (maxdeg >= kernels::big_degree) {
+          // a frontier may repeat a hub (SSSP), so the only safe bound on deferred items is nf
+          big_list = reinterpret_cast<vertex_t*>(scratch.temp(nf * sizeof(vertex_t)));
+        }
+        const unsigned grid = gcuda::persistent_grid(ctx, item_ctas, 6);
+        if (guard)
+          kernels::block_mapped_kernel<graph_input, has_output, true, policy>
+              <<<grid, 256, 0, stream>>>(A, op, in, nf, out, C, capacity, visited, big_list);
+        else
+          kernels::block_mapped_kernel<graph_input, has_output, false, policy>
+              <<<grid, 256, 0, stream>>>(A, op, in, nf, out, C, capacity, visited, big_list);
+        if (big_list) {
+          // (the hub kernel's capacity guard reads Σdeg, which is 0 = "fits" when it was not needed)
+          kernels::big_list_kernel<has_output, policy><<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(
+              A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
+        }
+      }
+    } else if constexpr (lb == load_balance_t::merge_path || lb == load_balance_t::merge_path_v2) {
+      if (segments.size() < nf + 1) segments.resize(nf + 1);
+      gcuda::arena_layout_t layout;
+      const std::size_t at_src = layout.add((nf + 1) * sizeof(vertex_t));
+      const std::size_t at_beg = layout.add((nf + 1) * sizeof(edge_t));
+      const std::size_t at_state = layout.add(2 * prep_tiles * sizeof(b200::tile_word_t));
+      unsigned char* base = scratch.temp(layout.bytes);
+      auto* work_src = reinterpret_cast<vertex_t*>(base + at_src);
+      auto* work_beg = reinterpret_cast<edge_t*>(base + at_beg);
+      auto* state = reinterpret_cast<b200::tile_word_t*>(base + at_state);
+      edge_t* work_seg = raw_of(segments.data());
+      cudaMemsetAsync(state, 0, 2 * prep_tiles * sizeof(b200::tile_word_t), stream);
+      kernels::prepare_work_kernel<graph_input><<<gcuda::persistent_grid(ctx, prep_tiles, 6), 256, 0, stream>>>(
+          A.offsets, in, nf, work_src, work_beg, work_seg, state, state + prep_tiles, C);
+      kernels::merge_path_kernel<has_output, policy>
+          <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(A, op, work_src, work_beg, work_seg,
+                                                                                out, C, capacity, visited);
+    } else if constexpr (lb == load_balance_t::bucketing) {
+      gcuda::arena_layout_t layout;
+      const std::size_t at_small = layout.add(nf * sizeof(vertex_t));
+      const std::size_t at_warp = layout.add(nf * sizeof(vertex_t));
+      const std::size_t at_big = layout.add(nf * sizeof(vertex_t));
+      unsigned char* base = scratch.temp(layout.bytes);
+      auto* small_list = reinterpret_cast<vertex_t*>(base + at_small);
+      auto* warp_list = reinterpret_cast<vertex_t*>(base + at_warp);
+      auto* big_list = reinterpret_cast<vertex_t*>(base + at_big);
+      kernels::bin_by_degree_kernel<graph_input><<<gcuda::persistent_grid(ctx, item_ctas, 8), 256, 0, stream>>>(
+          A.offsets, in, nf, small_list, warp_list, big_list, C);
+      kernels::thread_mapped_kernel<false, has_output, true, policy>
+          <<<gcuda::persistent_grid(ctx, item_ctas, 8), 256, 0, stream>>>(A, op, small_list, 0, C + scratch_t::aux0, out,
+                                                                        C, capacity, visited);
+      kernels::warp_mapped_kernel<has_output, policy>
+          <<<gcuda::persistent_grid(ctx, (nf + 7) / 8, 8), 256, 0, stream>>>(A, op, warp_list, C + scratch_t::aux1, out, C,
+                                                                            capacity, visited);
+      kernels::big_list_kernel<has_output, policy><<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(
+          A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
+    } else {
+      error::throw_if_exception(cudaErrorUnknown, "Advance type not supported.");
+    }
+    error::check_last("advance launch");
+    scratch.fetch(stream);
+    if constexpr (has_output) {
+      if (scratch.h[scratch_t::overflow]) {  // nothing was expanded: grow and go again
+        grow_output(output, std::size_t(scratch.h[scratch_t::overflow]));
+        continue;
+      }
+      output->set_number_of_elements(std::size_t(scratch.h[scratch_t::out_count]));
+    }
+    return;
+  }
+  error::throw_if_exception(cudaErrorMemoryAllocation, "advance: output frontier could not be sized");
+}
+
+/**
+ * @brief Direction-optimised advance (Beamer-style push/pull switching) on the enactor's dense state.
+ */
+template <load_balance_t lb, advance_io_type_t input_type, advance_io_type_t output_type, typename graph_t,
+          typename enactor_type, typename operator_t>
+void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_context_t& ctx) {
+  using vertex_t = typename graph_t::vertex_type;
+  using edge_t = typename graph_t::edge_type;
+  static_assert(input_type == advance_io_type_t::vertices && output_type == advance_io_type_t::vertices,
+                "direction-optimised advance maps a vertex frontier to a vertex frontier");
+  auto& D = E->direction;
+  auto& scratch = ctx.scratch();
+  auto stream = ctx.stream();
+  const auto out_adj = graph::adjacency_of<false>(G);
+  const auto in_adj = graph::adjacency_of<true>(G);
+  const vertex_t n = out_adj.n;
+  auto* input = E->get_input_frontier();
+  auto* output = E->get_output_frontier();
+
+  if (!D.initialised) {
+    D.visited.resize(std::size_t(n), stream);
+    D.dense[0].resize(std::size_t(n), stream);
+    D.dense[1].resize(std::size_t(n), stream);
+    const std::size_t nf = input->get_number_of_elements();
+    scratch.zero(stream);
+    kernels::init_visited_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 8), 256, 0, stream>>>(
+        in_adj.offsets, n, D.visited.data());
+    if (nf)
+      kernels::mark_frontier_kernel<<<gcuda::persistent_grid(ctx, (nf + 255) / 256, 8), 256, 0, stream>>>(
+          out_adj.offsets, input->data(), nf, nullptr, D.visited.data(), scratch.d);
+    scratch.fetch(stream);
+    D.frontier_edges = (long long)scratch.h[scratch_t::aux2];
+    D.unexplored_edges = (long long)out_adj.m - D.frontier_edges;
+    D.frontier_vertices = (long long)nf;
+    D.previous_frontier_vertices = 0;
+    D.frontier_is_dense = false;
+    D.pulling = false;
+    D.initialised = true;
+  }
+
+  // --- choose the direction for this level (Beamer, Asanovic, Patterson) ---
+  const float alpha = E->properties.direction_alpha, beta = E->properties.direction_beta;
+  if (!D.pulling) {
+    if (double(D.frontier_edges) > double(D.unexplored_edges) / double(alpha) &&
+        D.frontier_vertices > D.previous_frontier_vertices)
+      D.pulling = true;
+  } else {
+    if (double(D.frontier_vertices) < double(n) / double(beta) && D.frontier_vertices < D.previous_frontier_vertices)
+      D.pulling = false;
+  }
+
+  long long next_vertices = 0, next_edges = 0;
+  if (D.pulling) {
+    if (!D.frontier_is_dense) {  // sparse -> dense
+      frontier::convert(*input, D.dense[D.dense_selector], stream);
+      D.frontier_is_dense = true;
+    }
+    auto& cur = D.dense[D.dense_selector];
+    auto& nxt = D.dense[D.dense_selector ^ 1];
+    scratch.zero(stream);
+    kernels::pull_step_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 8), 256, 0, stream>>>(
+        in_adj, op, cur.data(), nxt.data(), D.visited.data(), scratch.d);
+    error::check_last("pull step");
+    scratch.fetch(stream);
+    next_vertices = (long long)scratch.h[scratch_t::out_count];
+    next_edges = (long long)scratch.h[scratch_t::aux2];
+    D.dense_selector ^= 1;
+    D.dense[D.dense_selector].set_number_of_elements(std::size_t(next_vertices));
+    output->set_number_of_elements(std::size_t(next_vertices));  // contents live in the dense map
+    ++D.pull_steps;
+  } else {
+    if (D.frontier_is_dense) {  // dense -> sparse
+      frontier::convert(D.dense[D.dense_selector], *input, ctx);
+      D.frontier_is_dense = false;
+    }
+    grow_output(output, std::size_t(n));
+    expand<lb, false, input_type, output_type, visit_t::test_and_set>(G, op, input, output, E->scanned_work_domain, ctx,
+                                                                     D.visited.data());
+    next_vertices = (long long)output->get_number_of_elements();
+    if (next_vertices) {
+      scratch.zero(stream);
+      kernels::mark_frontier_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(next_vertices) + 255) / 256, 8), 256, 0,
+                                      stream>>>(out_adj.offsets, output->data(), std::size_t(next_vertices), nullptr,
+                                                (unsigned*)nullptr, scratch.d);
+      scratch.fetch(stream);
+      next_edges = (long long)scratch.h[scratch_t::aux2];
+    }
+    ++D.push_steps;
+  }
+  D.previous_frontier_vertices = D.frontier_vertices;
+  D.frontier_vertices = next_vertices;
+  D.frontier_edges = next_edges;
+  D.unexplored_edges -= next_edges;
+}
+
+}  // namespace detail
+
+/**
+ * @brief Explicit-buffers form (reference advance.hxx:91-129; used by e.g. bc.hxx:140-146).
+ */
+template <load_balance_t lb, advance_direction_t direction, advance_io_type_t input_type,
+          advance_io_type_t output_type, typename graph_t, typename operator_t, typename frontier_t,
+          typename work_tiles_t>
+void execute(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, work_tiles_t& segments,
+             gcuda::multi_context_t& context) {
+  error::throw_if_exception(context.size() != 1, "`context.size() != 1` not supported");
+  auto* ctx = context.get_context(0);
+  if constexpr (direction == advance_direction_t::optimized) {
+    error::throw_if_exception(cudaErrorUnknown,
+                              "direction-optimized advance needs the enactor form (it keeps dense state in E)");
+  } else if constexpr (lb == load_balance_t::warp_mapped || lb == load_balance_t::work_stealing) {
+    error::throw_if_exception(cudaErrorUnknown, "Advance type not supported.");
+  } else {
+    detail::expand<lb, direction == advance_direction_t::backward, input_type, output_type,
+                   detail::visit_t::none>(G, op, input, output, segments, *ctx, nullptr);
+  }
+}
+
+/**
+ * @brief Enactor form (reference advance.hxx:192-221): reads E's input frontier, writes E's output
+ * frontier, swaps the buffers unless output_type == none or swap_buffers is false.
+ */
+template <load_balance_t lb = load_balance_t::merge_path,
+          advance_direction_t direction = advance_direction_t::forward,
+          advance_io_type_t input_type = advance_io_type_t::vertices,
+          advance_io_type_t output_type = advance_io_type_t::vertices, typename graph_t, typename enactor_type,
+          typename operator_type>
+void execute(graph_t& G, enactor_type* E, operator_type op, gcuda::multi_context_t& context, bool swap_buffers = true) {
+  if constexpr (direction == advance_direction_t::optimized) {
+    error::throw_if_exception(context.size() != 1, "`context.size() != 1` not supported");
+    using csr_v = typename graph_t::graph_csr_view_t;
+    using csc_v = typename graph_t::graph_csc_view_t;
+    static_assert(graph_t::template contains_representation<csr_v>() &&
+                      graph_t::template contains_representation<csc_v>(),
+                  "CSR and CSC representations are required for direction-optimized advance");
+    detail::optimized<lb, input_type, output_type>(G, E, op, *context.get_context(0));
+  } else {
+    execute<lb, direction, input_type, output_type>(G, op, E->get_input_frontier(), E->get_output_frontier(),
+                                                    E->scanned_work_domain, context);
+  }
+  if (swap_buffers && (output_type != advance_io_type_t::none)) E->swap_frontier_buffers();
+}
+
+}  // namespace advance
+}  // namespace operators
+}  // namespace gunrock

@@ -1,0 +1,482 @@
+/**
+ * @file kernels.cuh
+ * @brief Hand-written sm_100a kernels behind operators::advance (push direction).
+ *
+ * What the reference does per advance: a Thrust reduce/scan + blocking D2H, a cudaMalloc,
+ * one kernel whose threads binary-search 256 shared-memory degrees for every single edge, writes one
+ * output slot per edge (mostly -1 holes), a sync and a cudaFree
+ * (advance/block_mapped.hxx:38-147,155-205; advance/helpers.hxx:39-146; advance/thread_mapped.hxx:32-96;
+ * advance/merge_path.hxx:35-114 = mgpu::transform_lbs).
+ *
+ * Here every balancer funnels into the same two device routines:
+ *   - visit_edge():   load neighbour (read-only path), optional visited-bitmap pre-check (1 bit/vertex, L2
+ *                     resident), call the user operator exactly once with lvalues, optional test-and-set.
+ *   - expand_tile():  a CTA walks a tile of edges described by shared-memory (source, first edge, offset)
+ *                     triples; ITEMS independent column loads per thread are issued before any operator
+ *                     runs; survivors are compacted with ONE global atomic per CTA round (warp shuffle
+ *                     scans), so the output frontier has no holes and the next level reads |F| not Σdeg.
+ * The balancers differ only in how tiles are cut:
+ *   thread_mapped : one thread per frontier item (warp-uniform trip count, warp-aggregated appends)
+ *   block_mapped  : a CTA takes 256 consecutive frontier items, all their edges form its tile; items with
+ *                   degree >= big_degree are deferred to a grid-wide kernel (no single-CTA hub tail)
+ *   merge_path    : one fused pass scans degrees by decoupled look-back and compacts non-empty items;
+ *                   tiles are equal slices of the edge range, located by binary search on the scan
+ *   bucketing     : items are binned by degree into thread-, warp- and grid-mapped lists
+ * Kernels are persistent (grid = SMs x resident CTAs, grid-stride) and read work sizes from the device
+ * counter block, so the host never has to learn Σdeg before launching.
+ */
+#pragma once
+
+#include <gunrock/b200/warp.cuh>
+#include <gunrock/b200/lookback.cuh>
+#include <gunrock/cuda/context.hxx>
+#include <gunrock/graph/graph.hxx>
+#include <gunrock/util/type_limits.hxx>
+
+namespace gunrock {
+namespace operators {
+namespace advance {
+namespace kernels {
+
+using b200::counter_t;
+using gcuda::scratch_t;
+
+constexpr int cta_threads = 256;
+constexpr int tile_items = 4;                         // edges per thread per round
+constexpr int tile_edges = cta_threads * tile_items;  // 1024 edges per CTA round
+constexpr int prep_items = 4;                         // frontier items per thread in the preparation pass
+constexpr long long big_degree = 8192;                // adjacency lists this long are expanded grid-wide
+constexpr int warp_degree = 32;                       // bucketing: lists at least this long get a warp
+
+/// Visited-bitmap handling of an advance: `none` = reference semantics (operator runs on every edge).
+enum class visit_t { none, test_and_set };
+
+template <visit_t policy, typename vertex_t, typename edge_t, typename weight_t, typename operator_t>
+__device__ __forceinline__ bool visit_edge(const graph::adjacency_t<vertex_t, edge_t, weight_t>& A,
+                                           operator_t& op, vertex_t source, edge_t edge, vertex_t neighbor,
+                                           unsigned* __restrict__ visited) {
+  if constexpr (policy == visit_t::test_and_set) {
+    if ((visited[unsigned(neighbor) >> 5] >> (unsigned(neighbor) & 31u)) & 1u) return false;
+  }
+  weight_t weight = A.values ? __ldg(A.values + edge) : weight_t(1);
+  bool keep = op(source, neighbor, edge, weight);
+  if constexpr (policy == visit_t::test_and_set) {
+    if (keep) {
+      const unsigned bit = 1u << (unsigned(neighbor) & 31u);
+      keep = !(atomicOr(&visited[unsigned(neighbor) >> 5], bit) & bit);
+    }
+  }
+  return keep;
+}
+
+/// Shared-memory description of the work a CTA expands in one go.
+template <typename vertex_t, typename edge_t>
+struct tile_smem_t {
+  vertex_t src[tile_edges + 1];
+  edge_t beg[tile_edges + 1];
+  edge_t seg[tile_edges + 1];               // exclusive offsets of the segments inside the tile
+  counter_t append[cta_threads / 32 + 4];   // scratch of b200::cta_append
+  edge_t scan_e[cta_threads / 32 + 1];
+  unsigned scan_u[cta_threads / 32 + 1];
+  long long bcast[4];
+};
+
+/**
+ * @brief The CTA expands `n_edges` edges spread over `n_seg` non-empty segments held in shared memory.
+ * Edge r of the tile belongs to the last segment j with seg[j] <= r and is global edge beg[j] + r - seg[j].
+ * Consecutive threads take consecutive edges (coalesced column loads).
+ */
+template <bool has_output, visit_t policy, typename vertex_t, typename edge_t, typename weight_t, typename operator_t>
+__device__ __forceinline__ void expand_tile(const graph::adjacency_t<vertex_t, edge_t, weight_t>& A, operator_t& op,
+                                            tile_smem_t<vertex_t, edge_t>& sm, int n_seg, edge_t n_edges,
+                                            vertex_t* __restrict__ output, counter_t* counters, counter_t capacity,
+                                            unsigned* __restrict__ visited) {
+  for (edge_t round = 0; round < n_edges; round += tile_edges) {
+    vertex_t nbr[tile_items];
+    vertex_t src[tile_items];
+    edge_t eid[tile_items];
+    unsigned live = 0;
+#pragma unroll
+    for (int i = 0; i < tile_items; ++i) {
+      edge_t r = round + edge_t(i * cta_threads + threadIdx.x);
+      if (r < n_edges) {
+        int j = n_seg == 1 ? 0 : b200::upper_segment(sm.seg, n_seg, r);
+        src[i] = sm.src[j];
+        eid[i] = sm.beg[j] + (r - sm.seg[j]);
+        live |= 1u << i;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < tile_items; ++i)
+      if (live & (1u << i)) nbr[i] = __ldg(A.indices + eid[i]);
+    unsigned keep = 0;
+#pragma unroll
+    for (int i = 0; i < tile_items; ++i)
+      if (live & (1u << i))
+        if (visit_edge<policy>(A, op, src[i], eid[i], nbr[i], visited)) keep |= 1u << i;
+    if constexpr (has_output)
+      b200::cta_append<cta_threads, tile_items>(nbr, keep, output, counters + scratch_t::out_count, capacity,
+                                                sm.append);
+  }
+}
+
+/// Output-capacity guard shared by the expansion kernels: when the worst case (every edge kept) does not
+/// fit, nothing runs and the required size is reported, so the host can grow the buffer and relaunch
+/// WITHOUT any operator having been called twice.
+__device__ __forceinline__ bool output_fits(counter_t* counters, counter_t capacity) {
+  const counter_t worst = counters[scratch_t::work_total];
+  if (worst <= capacity) return true;
+  if (blockIdx.x == 0 && threadIdx.x == 0) counters[scratch_t::overflow] = worst;
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Σ degree of a frontier (only launched when nf * max_degree could exceed the output capacity).
+template <bool graph_input, typename vertex_t, typename edge_t>
+__global__ void __launch_bounds__(cta_threads)
+    degree_sum_kernel(const edge_t* __restrict__ offsets, const vertex_t* __restrict__ input, std::size_t input_size,
+                      counter_t* counters) {
+  counter_t mine = 0;
+  for (std::size_t i = std::size_t(blockIdx.x) * cta_threads + threadIdx.x; i < input_size;
+       i += std::size_t(gridDim.x) * cta_threads) {
+    vertex_t v = graph_input ? vertex_t(i) : input[i];
+    if (util::limits::is_valid(v)) mine += counter_t(offsets[v + 1] - offsets[v]);
+  }
+  mine = b200::warp_sum(mine);
+  if (b200::lane_id() == 0 && mine) atomicAdd(counters + scratch_t::work_total, mine);
+}
+
+/// Max degree of the graph (once per graph and context; cached by the host).
+template <typename vertex_t, typename edge_t>
+__global__ void __launch_bounds__(cta_threads)
+    max_degree_kernel(const edge_t* __restrict__ offsets, vertex_t n, counter_t* result) {
+  counter_t mine = 0;
+  for (std::size_t v = std::size_t(blockIdx.x) * cta_threads + threadIdx.x; v < std::size_t(n);
+       v += std::size_t(gridDim.x) * cta_threads) {
+    counter_t d = counter_t(offsets[v + 1] - offsets[v]);
+    mine = d > mine ? d : mine;
+  }
+  mine = b200::warp_max(mine);
+  if (b200::lane_id() == 0) atomicMax(result, mine);
+}
+
+// ------------------------------------------------------------------------------------------------
+// thread_mapped: one thread per frontier item. `size_ptr` (optional) overrides input_size with a device
+// value so the kernel can consume a list another kernel just produced (bucketing's small bin).
+template <bool graph_input, bool has_output, bool guard, visit_t policy, typename vertex_t, typename edge_t,
+          typename weight_t, typename operator_t>
+__global__ void __launch_bounds__(cta_threads)
+    thread_mapped_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op,
+                         const vertex_t* __restrict__ input, std::size_t input_size, const counter_t* size_ptr,
+                         vertex_t* __restrict__ output, counter_t* counters, counter_t capacity,
+                         unsigned* __restrict__ visited) {
+  if constexpr (has_output && guard)
+    if (!output_fits(counters, capacity)) return;
+  if (size_ptr) input_size = std::size_t(*size_ptr);
+  for (std::size_t base = std::size_t(blockIdx.x) * cta_threads; base < input_size;
+       base += std::size_t(gridDim.x) * cta_threads) {
+    const std::size_t i = base + threadIdx.x;
+    vertex_t v = gunrock::numeric_limits<vertex_t>::invalid();
+    edge_t beg = 0, deg = 0;
+    if (i < input_size) {
+      v = graph_input ? vertex_t(i) : input[i];
+      if (util::limits::is_valid(v)) {
+        beg = A.offsets[v];
+        deg = A.offsets[v + 1] - beg;
+      }
+    }
+    const edge_t trips = b200::warp_max(deg);  // warp-uniform loop so ballots see the whole warp
+    for (edge_t k = 0; k < trips; ++k) {
+      bool keep = false;
+      vertex_t nbr = 0;
+      if (k < deg) {
+        nbr = __ldg(A.indices + beg + k);
+        keep = visit_edge<policy>(A, op, v, edge_t(beg + k), nbr, visited);
+      }
+      if constexpr (has_output) {
+        const unsigned votes = __ballot_sync(b200::full_mask, keep);
+        if (votes) {
+          counter_t at = b200::warp_append_slot(keep, counters + scratch_t::out_count);
+          if (keep && at < capacity) output[at] = nbr;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp_mapped: one warp per list item, lanes stride the adjacency (coalesced). Used by bucketing's
+// medium bin; the list length comes from a device counter.
+template <bool has_output, visit_t policy, typename vertex_t, typename edge_t, typename weight_t, typename operator_t>
+__global__ void __launch_bounds__(cta_threads)
+    warp_mapped_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op,
+                       const vertex_t* __restrict__ list, const counter_t* size_ptr, vertex_t* __restrict__ output,
+                       counter_t* counters, counter_t capacity, unsigned* __restrict__ visited) {
+  if constexpr (has_output)
+    if (!output_fits(counters, capacity)) return;
+  const std::size_t count = std::size_t(*size_ptr);
+  const unsigned lane = b200::lane_id();
+  const std::size_t warps = (std::size_t(gridDim.x) * cta_threads) >> 5;
+  for (std::size_t item = (std::size_t(blockIdx.x) * cta_threads + threadIdx.x) >> 5; item < count; item += warps) {
+    vertex_t v = list[item];
+    const edge_t beg = A.offsets[v], end = A.offsets[v + 1];
+    for (edge_t e0 = beg; e0 < end; e0 += 32) {
+      const edge_t e = e0 + lane;
+      bool keep = false;
+      vertex_t nbr = 0;
+      if (e < end) {
+        nbr = __ldg(A.indices + e);
+        keep = visit_edge<policy>(A, op, v, e, nbr, visited);
+      }
+      if constexpr (has_output) {
+        const unsigned votes = __ballot_sync(b200::full_mask, keep);
+        if (votes) {
+          counter_t at = b200::warp_append_slot(keep, counters + scratch_t::out_count);
+          if (keep && at < capacity) output[at] = nbr;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block_mapped: a CTA owns 256 consecutive frontier items and every edge under them.
+template <bool graph_input, bool has_output, bool guard, visit_t policy, typename vertex_t, typename edge_t,
+          typename weight_t, typename operator_t>
+__global__ void __launch_bounds__(cta_threads)
+    block_mapped_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op,
+                        const vertex_t* __restrict__ input, std::size_t input_size, vertex_t* __restrict__ output,
+                        counter_t* counters, counter_t capacity, unsigned* __restrict__ visited,
+                        vertex_t* __restrict__ big_list) {
+  __shared__ tile_smem_t<vertex_t, edge_t> sm;
+  if constexpr (has_output && guard)
+    if (!output_fits(counters, capacity)) return;
+  for (std::size_t base = std::size_t(blockIdx.x) * cta_threads; base < input_size;
+       base += std::size_t(gridDim.x) * cta_threads) {
+    const std::size_t i = base + threadIdx.x;
+    vertex_t v = gunrock::numeric_limits<vertex_t>::invalid();
+    edge_t beg = 0, deg = 0;
+    if (i < input_size) {
+      v = graph_input ? vertex_t(i) : input[i];
+      if (util::limits::is_valid(v)) {
+        beg = A.offsets[v];
+        deg = A.offsets[v + 1] - beg;
+      }
+    }
+    if (big_list && deg >= edge_t(big_degree)) {  // hub: hand it to the grid-wide kernel
+      counter_t at = atomicAdd(counters + scratch_t::big_count, counter_t(1));
+      big_list[at] = v;
+      deg = 0;
+    }
+    unsigned n_seg;
+    edge_t n_edges;
+    const unsigned my_seg = b200::cta_exclusive_sum<cta_threads, unsigned>(deg > 0 ? 1u : 0u, n_seg, sm.scan_u);
+    const edge_t my_off = b200::cta_exclusive_sum<cta_threads, edge_t>(deg, n_edges, sm.scan_e);
+    if (deg > 0) {
+      sm.src[my_seg] = v;
+      sm.beg[my_seg] = beg;
+      sm.seg[my_seg] = my_off;
+    }
+    __syncthreads();
+    if (n_edges > 0)
+      expand_tile<has_output, policy>(A, op, sm, int(n_seg), n_edges, output, counters, capacity, visited);
+    __syncthreads();
+  }
+}
+
+/// Grid-wide expansion of the deferred hubs: every CTA strides the 1024-edge tiles of each listed vertex.
+template <bool has_output, visit_t policy, typename vertex_t, typename edge_t, typename weight_t, typename operator_t>
+__global__ void __launch_bounds__(cta_threads)
+    big_list_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op,
+                    const vertex_t* __restrict__ big_list, const counter_t* size_ptr, vertex_t* __restrict__ output,
+                    counter_t* counters, counter_t capacity, unsigned* __restrict__ visited) {
+  __shared__ tile_smem_t<vertex_t, edge_t> sm;
+  if constexpr (has_output)
+    if (!output_fits(counters, capacity)) return;
+  const std::size_t count = std::size_t(*size_ptr);
+  for (std::size_t item = 0; item < count; ++item) {
+    const vertex_t v = big_list[item];
+    const edge_t beg = A.offsets[v], deg = A.offsets[v + 1] - beg;
+    for (edge_t t0 = edge_t(blockIdx.x) * tile_edges; t0 < deg; t0 += edge_t(gridDim.x) * tile_edges) {
+      if (threadIdx.x == 0) {
+        sm.src[0] = v;
+        sm.beg[0] = beg + t0;
+        sm.seg[0] = 0;
+      }
+      __syncthreads();
+      const edge_t left = deg - t0;
+      expand_tile<has_output, policy>(A, op, sm, 1, left < edge_t(tile_edges) ? left : edge_t(tile_edges), output,
+                                      counters, capacity, visited);
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// merge_path, pass 1: fused validity filter + degree gather + device-wide scan + compaction.
+// Produces work_src[k], work_beg[k], work_seg[k] (exclusive Σdeg over the compacted, non-empty items, with
+// work_seg[K] = total), counters[items] = K, counters[work_total] = Σdeg. Stable (frontier order kept).
+template <bool graph_input, typename vertex_t, typename edge_t>
+__global__ void __launch_bounds__(cta_threads)
+    prepare_work_kernel(const edge_t* __restrict__ offsets, const vertex_t* __restrict__ input, std::size_t input_size,
+                        vertex_t* __restrict__ work_src, edge_t* __restrict__ work_beg, edge_t* __restrict__ work_seg,
+                        b200::tile_word_t* state_items, b200::tile_word_t* state_edges, counter_t* counters) {
+  constexpr int per_tile = cta_threads * prep_items;
+  __shared__ unsigned scan_u[cta_threads / 32 + 1];
+  __shared__ unsigned long long scan_e[cta_threads / 32 + 1];
+  __shared__ unsigned long long prefix[2];
+  __shared__ int s_tile;
+  const int n_tiles = int((input_size + per_tile - 1) / per_tile);
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = int(atomicAdd(counters + scratch_t::ticket, counter_t(1)));
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= n_tiles) break;
+    const std::size_t first = std::size_t(tile) * per_tile + std::size_t(threadIdx.x) * prep_items;
+    vertex_t v[prep_items];
+    edge_t beg[prep_items], deg[prep_items];
+    if constexpr (!graph_input) {
+      if (first + prep_items <= input_size && prep_items == 4 && sizeof(vertex_t) == 4) {
+        const int4 q = *reinterpret_cast<const int4*>(input + first);  // 128-bit frontier load
+        v[0] = vertex_t(q.x), v[1] = vertex_t(q.y), v[2] = vertex_t(q.z), v[3] = vertex_t(q.w);
+      } else {
+#pragma unroll
+        for (int k = 0; k < prep_items; ++k)
+          v[k] = first + k < input_size ? input[first + k] : gunrock::numeric_limits<vertex_t>::invalid();
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < prep_items; ++k)
+        v[k] = first + k < input_size ? vertex_t(first + k) : gunrock::numeric_limits<vertex_t>::invalid();
+    }
+    unsigned my_items = 0;
+    unsigned long long my_edges = 0;
+#pragma unroll
+    for (int k = 0; k < prep_items; ++k) {
+      beg[k] = 0, deg[k] = 0;
+      if (util::limits::is_valid(v[k])) {
+        beg[k] = offsets[v[k]];
+        deg[k] = offsets[v[k] + 1] - beg[k];
+      }
+      my_items += deg[k] > 0;
+      my_edges += (unsigned long long)deg[k];
+    }
+    unsigned tile_items_total;
+    unsigned long long tile_edges_total;
+    const unsigned items_before = b200::cta_exclusive_sum<cta_threads, unsigned>(my_items, tile_items_total, scan_u);
+    const unsigned long long edges_before =
+        b200::cta_exclusive_sum<cta_threads, unsigned long long>(my_edges, tile_edges_total, scan_e);
+    if (threadIdx.x < 32) {
+      const unsigned long long a = b200::lookback_exclusive(state_items, tile, tile_items_total);
+      const unsigned long long b = b200::lookback_exclusive(state_edges, tile, tile_edges_total);
+      if (threadIdx.x == 0) {
+        prefix[0] = a;
+        prefix[1] = b;
+      }
+    }
+    __syncthreads();
+    std::size_t at = std::size_t(prefix[0]) + items_before;
+    unsigned long long run = prefix[1] + edges_before;
+#pragma unroll
+    for (int k = 0; k < prep_items; ++k)
+      if (deg[k] > 0) {
+        work_src[at] = v[k];
+        work_beg[at] = beg[k];
+        work_seg[at] = edge_t(run);
+        ++at;
+        run += (unsigned long long)deg[k];
+      }
+    if (tile == n_tiles - 1 && threadIdx.x == 0) {
+      const unsigned long long K = prefix[0] + tile_items_total, T = prefix[1] + tile_edges_total;
+      counters[scratch_t::items] = K;
+      counters[scratch_t::work_total] = T;
+      work_seg[K] = edge_t(T);
+    }
+    __syncthreads();  // s_tile / prefix reuse
+  }
+}
+
+// merge_path, pass 2: equal slices of the edge range; each CTA finds its first/last segment by binary
+// search on the scanned offsets, stages the slice's segments in shared memory and expands the tile.
+template <bool has_output, visit_t policy, typename vertex_t, typename edge_t, typename weight_t, typename operator_t>
+__global__ void __launch_bounds__(cta_threads)
+    merge_path_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op,
+                      const vertex_t* __restrict__ work_src, const edge_t* __restrict__ work_beg,
+                      const edge_t* __restrict__ work_seg, vertex_t* __restrict__ output, counter_t* counters,
+                      counter_t capacity, unsigned* __restrict__ visited) {
+  __shared__ tile_smem_t<vertex_t, edge_t> sm;
+  if constexpr (has_output)
+    if (!output_fits(counters, capacity)) return;
+  const long long total = (long long)counters[scratch_t::work_total];
+  const long long n_items = (long long)counters[scratch_t::items];
+  for (long long g0 = (long long)blockIdx.x * tile_edges; g0 < total; g0 += (long long)gridDim.x * tile_edges) {
+    const long long g1 = g0 + tile_edges < total ? g0 + tile_edges : total;
+    if (threadIdx.x == 0 || threadIdx.x == 32) {  // two lanes of two warps search the slice ends in parallel
+      const long long key = threadIdx.x == 0 ? g0 : g1 - 1;
+      long long lo = 0, hi = n_items;  // work_seg[lo] <= key < work_seg[hi]
+      while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if ((long long)work_seg[mid] <= key)
+          lo = mid;
+        else
+          hi = mid;
+      }
+      sm.bcast[threadIdx.x ? 1 : 0] = lo;
+    }
+    __syncthreads();
+    const long long j0 = sm.bcast[0];
+    const int n_seg = int(sm.bcast[1] - j0) + 1;  // <= tile_edges because every staged segment is non-empty
+    for (int j = threadIdx.x; j < n_seg; j += cta_threads) {
+      const long long s = (long long)work_seg[j0 + j];
+      sm.src[j] = work_src[j0 + j];
+      sm.beg[j] = work_beg[j0 + j] + edge_t(s < g0 ? g0 - s : 0);  // first segment may start before the slice
+      sm.seg[j] = edge_t(s < g0 ? 0 : s - g0);
+    }
+    __syncthreads();
+    expand_tile<has_output, policy>(A, op, sm, n_seg, edge_t(g1 - g0), output, counters, capacity, visited);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bucketing, pass 1: bin valid non-empty items by degree (thread / warp / grid classes) and total Σdeg.
+template <bool graph_input, typename vertex_t, typename edge_t>
+__global__ void __launch_bounds__(cta_threads)
+    bin_by_degree_kernel(const edge_t* __restrict__ offsets, const vertex_t* __restrict__ input,
+                         std::size_t input_size, vertex_t* __restrict__ small_list, vertex_t* __restrict__ warp_list,
+                         vertex_t* __restrict__ big_list, counter_t* counters) {
+  counter_t my_edges = 0;
+  for (std::size_t base = std::size_t(blockIdx.x) * cta_threads; base < input_size;
+       base += std::size_t(gridDim.x) * cta_threads) {
+    const std::size_t i = base + threadIdx.x;
+    edge_t deg = 0;
+    vertex_t v = 0;
+    if (i < input_size) {
+      v = graph_input ? vertex_t(i) : input[i];
+      if (util::limits::is_valid(v)) deg = offsets[v + 1] - offsets[v];
+    }
+    my_edges += counter_t(deg);
+    const bool is_big = deg >= edge_t(big_degree);
+    const bool is_warp = !is_big && deg >= edge_t(warp_degree);
+    const bool is_small = deg > 0 && deg < edge_t(warp_degree);
+    if (__ballot_sync(b200::full_mask, is_small)) {
+      counter_t at = b200::warp_append_slot(is_small, counters + scratch_t::aux0);
+      if (is_small) small_list[at] = v;
+    }
+    if (__ballot_sync(b200::full_mask, is_warp)) {
+      counter_t at = b200::warp_append_slot(is_warp, counters + scratch_t::aux1);
+      if (is_warp) warp_list[at] = v;
+    }
+    if (__ballot_sync(b200::full_mask, is_big)) {
+      counter_t at = b200::warp_append_slot(is_big, counters + scratch_t::big_count);
+      if (is_big) big_list[at] = v;
+    }
+  }
+  my_edges = b200::warp_sum(my_edges);
+  if (b200::lane_id() == 0 && my_edges) atomicAdd(counters + scratch_t::work_total, my_edges);
+}
+
+}  // namespace kernels
+}  // namespace advance
+}  // namespace operators
+}  // namespace gunrock

@@ -1,0 +1,181 @@
+/**
+ * @file build.hxx
+ * @brief graph::build::from_csr — wraps caller-owned CSR arrays into a graph_t and, when asked, derives
+ * the COO row indices or the CSC (transpose) into caller-provided buffers.
+ *
+ * Signature kept from the reference (include/gunrock/graph/build.hxx:21-36):
+ *   from_csr<space, views>(rows, cols, nnz, Ap, J, X, I = nullptr, Aj = nullptr)
+ * with I = row_indices[nnz] and Aj = column_offsets[rows+1]. Unlike the reference
+ * (graph/detail/build.hxx:85-111) CSR|CSC together is supported and the CSR arrays are never modified:
+ * the transpose is a counting sort by column (histogram -> scan -> cursor scatter) that fills I and Aj and,
+ * for weighted graphs, a separate `csc_values` array (extra trailing parameter). Passing I == J and
+ * Aj == Ap declares the graph symmetric: the CSC view then aliases the CSR arrays (exact for undirected
+ * graphs, zero cost). Host-space graphs are wrapped as-is.
+ * Setup code: runs once per graph, outside every timed region.
+ */
+#pragma once
+
+#include <type_traits>
+#include <cuda_runtime_api.h>
+#include <gunrock/error.hxx>
+#include <gunrock/memory.hxx>
+
+namespace gunrock {
+namespace graph {
+namespace build {
+namespace detail {
+
+template <typename edge_t>
+__device__ __forceinline__ edge_t bump(edge_t* p) {
+  if constexpr (sizeof(edge_t) == 8)
+    return edge_t(atomicAdd(reinterpret_cast<unsigned long long*>(p), 1ull));
+  else
+    return edge_t(atomicAdd(reinterpret_cast<unsigned int*>(p), 1u));
+}
+
+template <typename vertex_t, typename edge_t>
+__global__ void __launch_bounds__(256) rows_of_edges_kernel(vertex_t n, const edge_t* __restrict__ offsets,
+                                                           vertex_t* __restrict__ row_of_edge) {
+  const unsigned lane = threadIdx.x & 31;
+  const std::size_t warps = (std::size_t(gridDim.x) * blockDim.x) >> 5;
+  for (std::size_t row = (std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < std::size_t(n); row += warps) {
+    edge_t b = offsets[row], e = offsets[row + 1];
+    for (edge_t k = b + lane; k < e; k += 32) row_of_edge[k] = vertex_t(row);
+  }
+}
+
+template <typename vertex_t, typename edge_t>
+__global__ void __launch_bounds__(256) column_histogram_kernel(edge_t m, const vertex_t* __restrict__ columns,
+                                                              edge_t* __restrict__ counts_shifted) {
+  for (std::size_t e = std::size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < std::size_t(m);
+       e += std::size_t(gridDim.x) * blockDim.x)
+    bump(&counts_shifted[columns[e] + 1]);
+}
+
+/// In-place inclusive scan of a[0..count) by ONE CTA walking 1024-element chunks (setup only).
+template <typename edge_t>
+__global__ void __launch_bounds__(1024) single_cta_inclusive_scan_kernel(edge_t* a, std::size_t count) {
+  __shared__ edge_t warp_sums[33];
+  __shared__ edge_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (std::size_t base = 0; base < count; base += 1024) {
+    std::size_t i = base + threadIdx.x;
+    edge_t x = i < count ? a[i] : edge_t(0);
+    for (int d = 1; d < 32; d <<= 1) {
+      edge_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= unsigned(d)) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      edge_t w = warp_sums[lane];
+      for (int d = 1; d < 32; d <<= 1) {
+        edge_t y = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= unsigned(d)) w += y;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    edge_t before = carry + (warp ? warp_sums[warp - 1] : edge_t(0));
+    if (i < count) a[i] = x + before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = x + before;
+    __syncthreads();
+  }
+}
+
+template <typename vertex_t, typename edge_t, typename weight_t>
+__global__ void __launch_bounds__(256)
+    transpose_scatter_kernel(vertex_t n, const edge_t* __restrict__ offsets, const vertex_t* __restrict__ columns,
+                             const weight_t* __restrict__ values, edge_t* __restrict__ cursor,
+                             vertex_t* __restrict__ row_indices, weight_t* __restrict__ csc_values) {
+  const unsigned lane = threadIdx.x & 31;
+  const std::size_t warps = (std::size_t(gridDim.x) * blockDim.x) >> 5;
+  for (std::size_t row = (std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < std::size_t(n); row += warps) {
+    edge_t b = offsets[row], e = offsets[row + 1];
+    for (edge_t k = b + lane; k < e; k += 32) {
+      edge_t at = bump(&cursor[columns[k]]);
+      row_indices[at] = vertex_t(row);
+      if (csc_values) csc_values[at] = values ? values[k] : weight_t(1);
+    }
+  }
+}
+
+template <typename vertex_t, typename edge_t, typename weight_t>
+void transpose_on_device(vertex_t n, edge_t m, const edge_t* Ap, const vertex_t* J, const weight_t* X,
+                         vertex_t* I, edge_t* Aj, weight_t* csc_values) {
+  error::throw_if_exception(cudaMemset(Aj, 0, sizeof(edge_t) * (std::size_t(n) + 1)), "transpose memset");
+  if (m > 0) column_histogram_kernel<<<2048, 256>>>(m, J, Aj);
+  single_cta_inclusive_scan_kernel<<<1, 1024>>>(Aj, std::size_t(n) + 1);
+  memory::device_array_t<edge_t> cursor(std::size_t(n) + 1);
+  error::throw_if_exception(
+      cudaMemcpy(cursor.data(), Aj, sizeof(edge_t) * (std::size_t(n) + 1), cudaMemcpyDeviceToDevice),
+      "transpose cursor");
+  transpose_scatter_kernel<<<2048, 256>>>(n, Ap, J, X, cursor.data(), I, csc_values);
+  error::throw_if_exception(cudaDeviceSynchronize(), "transpose");
+}
+
+}  // namespace detail
+
+template <memory_space_t space, view_t build_views, typename edge_t, typename vertex_t, typename weight_t>
+auto from_csr(vertex_t const& r, vertex_t const& c, edge_t const& nnz, edge_t* Ap, vertex_t* J, weight_t* X,
+              vertex_t* I = nullptr, edge_t* Aj = nullptr, weight_t* csc_values = nullptr) {
+  constexpr bool want_csr = has(build_views, view_t::csr);
+  constexpr bool want_csc = has(build_views, view_t::csc);
+  constexpr bool want_coo = has(build_views, view_t::coo);
+  static_assert(!(want_csc && want_coo), "CSC and COO views share the row-index buffer; build one of them");
+
+  using csr_v_t = std::conditional_t<want_csr, graph_csr_t<vertex_t, edge_t, weight_t>, empty_csr_t>;
+  using csc_v_t = std::conditional_t<want_csc, graph_csc_t<vertex_t, edge_t, weight_t>, empty_csc_t>;
+  using coo_v_t = std::conditional_t<want_coo, graph_coo_t<vertex_t, edge_t, weight_t>, empty_coo_t>;
+  using graph_type = graph_t<space, vertex_t, edge_t, weight_t, csr_v_t, csc_v_t, coo_v_t>;
+
+  graph_type G;
+  if constexpr (want_csr) G.template set<csr_v_t>(r, nnz, Ap, J, X);
+
+  if constexpr (want_coo) {
+    error::throw_if_exception(I == nullptr, "from_csr: COO view needs a row_indices buffer");
+    if constexpr (space == memory_space_t::device) {
+      detail::rows_of_edges_kernel<<<2048, 256>>>(r, Ap, I);
+      error::throw_if_exception(cudaDeviceSynchronize(), "from_csr coo");
+    } else {
+      for (vertex_t row = 0; row < r; ++row)
+        for (edge_t e = Ap[row]; e < Ap[row + 1]; ++e) I[e] = row;
+    }
+    G.template set<coo_v_t>(r, nnz, I, J, X);
+  }
+
+  if constexpr (want_csc) {
+    error::throw_if_exception(I == nullptr || Aj == nullptr,
+                              "from_csr: CSC view needs row_indices and column_offsets buffers");
+    if (I == J && Aj == Ap) {  // declared symmetric: alias, nothing to compute
+      G.get_properties().symmetric = true;
+      G.template set<csc_v_t>(r, nnz, Ap, J, X);
+    } else {
+      static_assert(space == memory_space_t::device || !want_csc, "CSC build runs on the device");
+      detail::transpose_on_device(r, nnz, Ap, J, X, I, Aj, csc_values);
+      G.template set<csc_v_t>(r, nnz, Aj, I, csc_values);
+    }
+  }
+  (void)c;
+  return G;
+}
+
+/// Wrap pre-built CSR and CSC arrays (no computation): used by the C ABI when the caller owns both.
+template <typename vertex_t, typename edge_t, typename weight_t>
+auto from_csr_and_csc(vertex_t n, edge_t m, edge_t* Ap, vertex_t* J, weight_t* X, edge_t* Aj, vertex_t* I,
+                      weight_t* Xt) {
+  using csr_v_t = graph_csr_t<vertex_t, edge_t, weight_t>;
+  using csc_v_t = graph_csc_t<vertex_t, edge_t, weight_t>;
+  graph_t<memory_space_t::device, vertex_t, edge_t, weight_t, csr_v_t, csc_v_t, empty_coo_t> G;
+  G.template set<csr_v_t>(n, m, Ap, J, X);
+  G.template set<csc_v_t>(n, m, Aj, I, Xt);
+  G.get_properties().symmetric = (Aj == Ap && I == J);
+  return G;
+}
+
+}  // namespace build
+}  // namespace graph
+}  // namespace gunrock

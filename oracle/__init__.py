@@ -1,0 +1,239 @@
+"""CPU checker for the frontier-operator hot path — TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this package. ``essentials_b200`` never does: the product has no CPU path.
+
+Two libraries, both driven through ctypes on numpy arrays:
+
+* ``liboracle.so``  — our restatement (``oracle.cpp``), always buildable (g++ only).
+* ``_ref/libref_cpu.so`` — the reference's own ``*_cpu.hxx`` compiled from ``/root/reference`` by
+  ``oracle/Makefile`` (int32 offsets only, single threaded).  Prebuilt here and shipped to the GPU box
+  as a binary; ``/root/reference`` itself is never read at test/bench run time.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_float, c_int, c_int32, c_int64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_SO = os.path.join(_HERE, "liboracle.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libref_cpu.so")
+
+
+def build(verbose: bool = False) -> None:
+    """(Re)build the checker libraries; the reference build is skipped when /root/reference is absent."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-s", "-f", os.path.join(_HERE, "Makefile"), "all"], stdout=out)
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+def _i64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f32(a) -> np.ndarray | None:
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+_lib = None
+_ref = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        src = os.path.join(_HERE, "oracle.cpp")
+        if not os.path.exists(_ORACLE_SO) or os.path.getmtime(_ORACLE_SO) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-f", os.path.join(_HERE, "Makefile"), _ORACLE_SO])
+        L = ctypes.CDLL(_ORACLE_SO)
+        L.oracle_bfs.restype = c_float
+        L.oracle_bfs.argtypes = [c_int64, c_void_p, c_void_p, c_int32, c_void_p]
+        L.oracle_sssp.restype = c_float
+        L.oracle_sssp.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+        L.oracle_pr.restype = c_int
+        L.oracle_pr.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int,
+                                c_void_p, c_void_p]
+        L.oracle_ppr.restype = c_float
+        L.oracle_ppr.argtypes = [c_int64, c_void_p, c_void_p, c_int32, c_float, c_float, c_void_p]
+        L.oracle_kcore.restype = c_float
+        L.oracle_kcore.argtypes = [c_int64, c_void_p, c_void_p, c_void_p]
+        L.oracle_randoms.restype = None
+        L.oracle_randoms.argtypes = [c_int64, c_float, c_float, c_void_p]
+        L.oracle_color_jacobi.restype = c_int
+        L.oracle_color_jacobi.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.oracle_color_errors.restype = c_int64
+        L.oracle_color_errors.argtypes = [c_int64, c_void_p, c_void_p, c_void_p]
+        L.oracle_reached_i32.restype = None
+        L.oracle_reached_i32.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+        _lib = L
+    return _lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(_REF_SO)
+
+
+def ref() -> ctypes.CDLL:
+    """The reference's own CPU code (oracle/_ref). Raises if it was never built."""
+    global _ref
+    if _ref is None:
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libref_cpu.so missing: run `make -C oracle` where /root/reference exists")
+        R = ctypes.CDLL(_REF_SO)
+        for name in ("ref_bfs", "ref_sssp", "ref_kcore", "ref_ppr", "ref_color"):
+            getattr(R, name).restype = c_float
+        R.ref_bfs.argtypes = [c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]
+        R.ref_sssp.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+        R.ref_kcore.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p]
+        R.ref_ppr.argtypes = [c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_float, c_float]
+        R.ref_color.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p]
+        R.ref_randoms.restype = None
+        R.ref_randoms.argtypes = [c_int, c_float, c_float, c_void_p]
+        R.ref_load_mtx.restype = c_int
+        R.ref_free.argtypes = [c_void_p]
+        _ref = R
+    return _ref
+
+
+# ----------------------------------------------------------------------------- our restatement
+def bfs(off, col, src: int, return_ms: bool = False):
+    off, col = _i64(off), _i32(col)
+    n = off.size - 1
+    depth = np.empty(n, np.int32)
+    ms = lib().oracle_bfs(n, _ptr(off), _ptr(col), int(src), _ptr(depth))
+    return (depth, ms) if return_ms else depth
+
+
+def sssp(off, col, w, src: int, return_ms: bool = False):
+    off, col, w = _i64(off), _i32(col), _f32(w)
+    n = off.size - 1
+    dist = np.empty(n, np.float32)
+    ms = lib().oracle_sssp(n, _ptr(off), _ptr(col), _ptr(w), int(src), _ptr(dist))
+    return (dist, ms) if return_ms else dist
+
+
+def pagerank(off, col, w=None, alpha=0.85, tol=1e-6, force_iters=0, max_iters=1000, return_ms=False):
+    off, col, w = _i64(off), _i32(col), _f32(w)
+    n = off.size - 1
+    p = np.empty(n, np.float32)
+    ms = c_float(0)
+    it = lib().oracle_pr(n, _ptr(off), _ptr(col), _ptr(w), alpha, tol, force_iters, max_iters, _ptr(p),
+                         ctypes.addressof(ms))
+    return (p, it, ms.value) if return_ms else (p, it)
+
+
+def ppr(off, col, seed: int, alpha=0.15, eps=1e-6):
+    off, col = _i64(off), _i32(col)
+    n = off.size - 1
+    p = np.zeros(n, np.float32)
+    lib().oracle_ppr(n, _ptr(off), _ptr(col), int(seed), alpha, eps, _ptr(p))
+    return p
+
+
+def kcore(off, col):
+    off, col = _i64(off), _i32(col)
+    n = off.size - 1
+    core = np.empty(n, np.int32)
+    lib().oracle_kcore(n, _ptr(off), _ptr(col), _ptr(core))
+    return core
+
+
+def randoms(n: int, lo: float, hi: float):
+    out = np.empty(n, np.float32)
+    lib().oracle_randoms(n, lo, hi, _ptr(out))
+    return out
+
+
+def color_jacobi(off, col, rnd=None):
+    off, col = _i64(off), _i32(col)
+    n = off.size - 1
+    rnd = randoms(n, 0.0, float(n)) if rnd is None else _f32(rnd)
+    color = np.empty(n, np.int32)
+    it = lib().oracle_color_jacobi(n, _ptr(off), _ptr(col), _ptr(rnd), _ptr(color))
+    return color, it
+
+
+def color_errors(off, col, color) -> int:
+    off, col, color = _i64(off), _i32(col), _i32(color)
+    return int(lib().oracle_color_errors(off.size - 1, _ptr(off), _ptr(col), _ptr(color)))
+
+
+def reached(off, depth):
+    off, depth = _i64(off), _i32(depth)
+    nr, mr = c_int64(0), c_int64(0)
+    lib().oracle_reached_i32(off.size - 1, _ptr(off), _ptr(depth), ctypes.addressof(nr), ctypes.addressof(mr))
+    return nr.value, mr.value
+
+
+# ----------------------------------------------------------------------------- the reference's own CPU code
+def ref_load_mtx(path: str):
+    R = ref()
+    n, m = c_int(), c_int()
+    off, col = ctypes.POINTER(c_int)(), ctypes.POINTER(c_int)()
+    val = ctypes.POINTER(c_float)()
+    R.ref_load_mtx(path.encode(), ctypes.byref(n), ctypes.byref(m), ctypes.byref(off), ctypes.byref(col),
+                   ctypes.byref(val))
+    o = np.ctypeslib.as_array(off, (n.value + 1,)).copy()
+    c = np.ctypeslib.as_array(col, (m.value,)).copy()
+    v = np.ctypeslib.as_array(val, (m.value,)).copy()
+    for p in (off, col, val):
+        R.ref_free(ctypes.cast(p, c_void_p))
+    return o, c, v
+
+
+def _ref_csr(off, col):
+    off, col = _i32(off), _i32(col)
+    return off, col, off.size - 1, col.size
+
+
+def ref_bfs(off, col, src: int, return_ms=False):
+    off, col, n, m = _ref_csr(off, col)
+    d = np.empty(n, np.int32)
+    ms = ref().ref_bfs(n, m, _ptr(off), _ptr(col), int(src), _ptr(d))
+    return (d, ms) if return_ms else d
+
+
+def ref_sssp(off, col, w, src: int, return_ms=False):
+    off, col, n, m = _ref_csr(off, col)
+    w = _f32(w)
+    d = np.empty(n, np.float32)
+    ms = ref().ref_sssp(n, m, _ptr(off), _ptr(col), _ptr(w), int(src), _ptr(d))
+    return (d, ms) if return_ms else d
+
+
+def ref_kcore(off, col):
+    off, col, n, m = _ref_csr(off, col)
+    k = np.empty(n, np.int32)
+    ref().ref_kcore(n, m, _ptr(off), _ptr(col), _ptr(k))
+    return k
+
+
+def ref_ppr(off, col, n_seeds: int, alpha=0.15, eps=1e-6):
+    off, col, n, m = _ref_csr(off, col)
+    p = np.zeros((n_seeds, n), np.float32)
+    ref().ref_ppr(n, m, _ptr(off), _ptr(col), int(n_seeds), _ptr(p), alpha, eps)
+    return p
+
+
+def ref_color(off, col):
+    off, col, n, m = _ref_csr(off, col)
+    c = np.empty(n, np.int32)
+    ref().ref_color(n, m, _ptr(off), _ptr(col), _ptr(c))
+    return c
+
+
+def ref_randoms(n: int, lo: float, hi: float):
+    out = np.empty(n, np.float32)
+    ref().ref_randoms(n, lo, hi, _ptr(out))
+    return out

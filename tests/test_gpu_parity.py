@@ -1,0 +1,289 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the oracle and the golden vectors.
+
+Bars: BFS depths, k-core numbers, colours, operator outputs — bit-exact. SSSP — bit-exact (stronger than the
+1e-6 relative north_star asks). PageRank pull — 1e-6 relative; PageRank push (unordered float atomics, like
+the reference) — 1e-6 relative in L1 and 1e-4 per element. PPR — 1e-6 absolute, the reference driver's own
+tolerance (examples/algorithms/ppr/ppr.cu:76-79)."""
+import numpy as np
+import pytest
+import torch
+
+import essentials_b200 as ess
+import oracle
+from essentials_b200 import graphgen as gg
+
+pytestmark = pytest.mark.gpu
+
+LBS = list(ess.IMPLEMENTED_LOAD_BALANCERS)
+INF = 2**31 - 1
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    assert torch.cuda.is_available(), "GPU suite needs a CUDA device"
+    return ess.Context(0)
+
+
+def csr_from_golden(g, wide=False):
+    off = torch.from_numpy(g["offsets"].astype(np.int64 if wide else np.int32)).cuda()
+    return gg.CSR(off.numel() - 1, g["indices"].size, off, torch.from_numpy(g["indices"]).cuda(),
+                  torch.from_numpy(g["values"]).cuda(), "golden", True)
+
+
+@pytest.fixture(scope="module")
+def graphs(golden):
+    return {k: ess.Graph(csr_from_golden(v)) for k, v in golden.items()}
+
+
+@pytest.fixture(scope="module")
+def s16():
+    csr = gg.rmat_csr(16, device="cuda")
+    return csr, ess.Graph(csr), csr.host()
+
+
+# ------------------------------------------------------------------------------------------------ BFS
+@pytest.mark.parametrize("direction", ["forward", "optimized"])
+@pytest.mark.parametrize("lb", LBS)
+@pytest.mark.parametrize("name", ["chesapeake", "rmat_s10", "grid_24x17"])
+def test_bfs_golden(ctx, graphs, golden, name, lb, direction):
+    for s in golden[name]["sources"]:
+        depth, info = ess.bfs(ctx, graphs[name], int(s), lb=lb, direction=direction)
+        assert np.array_equal(depth.cpu().numpy(), golden[name][f"bfs_{s}"]), (name, lb, direction, int(s))
+        assert info["iterations"] >= 1
+
+
+@pytest.mark.parametrize("direction", ["forward", "optimized"])
+@pytest.mark.parametrize("lb", LBS)
+def test_bfs_config1_rmat_scale16(ctx, s16, lb, direction):
+    """BASELINE config 1: RMAT scale-16 ef-16 vs the CPU reference; source 0 (what the reference driver
+    hard-codes, bfs.cu:62) and seeded non-isolated sources."""
+    csr, g, (off, col, _) = s16
+    for s in [0] + gg.pick_sources(csr, 3):
+        depth, info = ess.bfs(ctx, g, s, lb=lb, direction=direction)
+        assert np.array_equal(depth.cpu().numpy(), oracle.bfs(off, col, s)), (lb, direction, s)
+    if direction == "optimized":
+        assert info["pull_steps"] >= 1, "a Kronecker graph must trigger the bottom-up switch"
+
+
+def test_bfs_int64_offsets(ctx, golden):
+    g = ess.Graph(csr_from_golden(golden["rmat_s10"], wide=True))
+    for lb in LBS:
+        for direction in ("forward", "optimized"):
+            s = int(golden["rmat_s10"]["sources"][0])
+            depth, _ = ess.bfs(ctx, g, s, lb=lb, direction=direction)
+            assert np.array_equal(depth.cpu().numpy(), golden["rmat_s10"][f"bfs_{s}"])
+
+
+def test_bfs_isolated_source_and_errors(ctx, s16):
+    csr, g, (off, col, _) = s16
+    iso = int(torch.nonzero(csr.degrees() == 0)[0])
+    for direction in ("forward", "optimized"):
+        depth, info = ess.bfs(ctx, g, iso, direction=direction)
+        d = depth.cpu().numpy()
+        assert d[iso] == 0 and (d != INF).sum() == 1
+    with pytest.raises(ess.EssentialsError):
+        ess.bfs(ctx, g, csr.n)  # source out of range
+    with pytest.raises(ess.EssentialsError):
+        ess.bfs(ctx, g, 0, lb="warp_mapped")  # "Advance type not supported." like the reference
+    directed = ess.Graph(gg.rmat_csr(8, symmetric=False, device="cuda"))
+    with pytest.raises(ess.EssentialsError):
+        ess.bfs(ctx, directed, 0, direction="optimized")  # needs CSR and CSC
+
+
+def test_bfs_large_properties(ctx):
+    """Size-independent checks at a scale the CPU oracle is not needed for (scale-20): all variants agree,
+    every edge spans at most one level, every reached non-source vertex has a parent one level up."""
+    csr = gg.rmat_csr(20, device="cuda")
+    g = ess.Graph(csr)
+    s = gg.pick_sources(csr, 1)[0]
+    base, _ = ess.bfs(ctx, g, s, lb="block_mapped", direction="forward")
+    for lb in LBS:
+        d2, info = ess.bfs(ctx, g, s, lb=lb, direction="optimized")
+        assert torch.equal(base, d2), lb
+    rows = torch.repeat_interleave(torch.arange(csr.n, device="cuda"), csr.degrees().long())
+    du, dv = base[rows].long(), base[csr.indices.long()].long()
+    assert bool(((du == INF) == (dv == INF)).all()), "reached set is closed under edges"
+    ok = du != INF
+    assert int((du[ok] - dv[ok]).abs().max()) <= 1
+    has_parent = torch.zeros(csr.n, dtype=torch.bool, device="cuda")
+    has_parent[rows[ok & (dv == du - 1)]] = True
+    reached = base != INF
+    reached[s] = False
+    assert bool(has_parent[reached].all())
+
+
+# ------------------------------------------------------------------------------------------------ SSSP
+@pytest.mark.parametrize("lb", LBS)
+@pytest.mark.parametrize("name", ["chesapeake", "rmat_s10", "grid_24x17"])
+def test_sssp_golden_bit_exact(ctx, graphs, golden, name, lb):
+    for s in golden[name]["sources"]:
+        dist, _ = ess.sssp(ctx, graphs[name], int(s), lb=lb)
+        assert np.array_equal(dist.cpu().numpy(), golden[name][f"sssp_{s}"]), (name, lb, int(s))
+
+
+@pytest.mark.parametrize("lb", ["block_mapped", "merge_path", "bucketing"])
+def test_sssp_rmat14_and_grid(ctx, lb):
+    csr = gg.rmat_csr(14, weights="hash", device="cuda")
+    off, col, val = csr.host()
+    g = ess.Graph(csr)
+    for s in gg.pick_sources(csr, 2):
+        dist, _ = ess.sssp(ctx, g, s, lb=lb)
+        want = oracle.sssp(off, col, val, s)
+        got = dist.cpu().numpy()
+        assert np.array_equal(got, want), f"max rel err {np.max(np.abs(got - want) / np.maximum(want, 1e-30))}"
+    grid = gg.grid_csr(96, 80, device="cuda")
+    off, col, val = grid.host()
+    dist, info = ess.sssp(ctx, ess.Graph(grid), 0, lb=lb)
+    assert np.array_equal(dist.cpu().numpy(), oracle.sssp(off, col, val, 0))
+    assert info["iterations"] >= 96 + 80 - 2
+
+
+# ------------------------------------------------------------------------------------------------ PageRank
+@pytest.mark.parametrize("mode", ["pull", "block_mapped", "merge_path", "bucketing", "thread_mapped"])
+def test_pagerank_directed_rmat(ctx, mode):
+    """BASELINE config 4 shape at scale-12: directed RMAT, weights 1, alpha .85, tol 1e-6 (pr.cu:55-56)."""
+    csr = gg.rmat_csr(12, symmetric=False, weights="ones", device="cuda")
+    off, col, val = csr.host()
+    csc = ess.transpose(csr)
+    g = ess.Graph(csr, csc=csc)
+    pull = mode == "pull"
+    p, info = ess.pagerank(ctx, g, lb="block_mapped" if pull else mode, pull=pull)
+    got = p.cpu().numpy().astype(np.float64)
+    _, it_cpu = oracle.pagerank(off, col, val)
+    assert abs(info["iterations"] - it_cpu) <= 1, (info, it_cpu)
+    want = oracle.pagerank(off, col, val, force_iters=info["iterations"])[0].astype(np.float64)
+    assert abs(got.sum() - 1.0) < 1e-4
+    rel_l1 = np.abs(got - want).sum() / want.sum()
+    assert rel_l1 < 1e-6, rel_l1
+    rtol = 1e-6 if pull else 1e-4  # push sums with unordered float atomics, exactly like the reference
+    assert np.allclose(got, want, rtol=rtol, atol=0), np.max(np.abs(got - want) / want)
+
+
+# ------------------------------------------------------------------------------------------------ PPR
+@pytest.mark.parametrize("lb", LBS)
+def test_ppr_golden(ctx, graphs, golden, lb):
+    for name in ("chesapeake", "rmat_s10"):
+        for s in golden[name]["ppr_seeds"]:
+            p, _ = ess.ppr(ctx, graphs[name], int(s), lb=lb)
+            err = np.abs(p.cpu().numpy() - golden[name][f"ppr_{s}"]).max()
+            assert err <= 1e-6, (name, lb, int(s), err)
+
+
+# ------------------------------------------------------------------------------------------------ k-core / colouring
+@pytest.mark.parametrize("lb", LBS)
+def test_kcore_golden(ctx, graphs, golden, lb):
+    for name in ("chesapeake", "rmat_s10", "grid_24x17"):
+        k, _ = ess.kcore(ctx, graphs[name], lb=lb)
+        assert np.array_equal(k.cpu().numpy(), golden[name]["kcore"]), (name, lb)
+
+
+def test_kcore_rmat12(ctx):
+    csr = gg.rmat_csr(12, device="cuda")
+    off, col, _ = csr.host()
+    k, _ = ess.kcore(ctx, ess.Graph(csr), lb="merge_path")
+    assert np.array_equal(k.cpu().numpy(), oracle.kcore(off, col))
+
+
+def test_randoms_and_color(ctx, graphs, golden, s16):
+    for name in ("chesapeake", "rmat_s10", "grid_24x17"):
+        n = golden[name]["offsets"].size - 1
+        r = ess.randoms(ctx, n, 0.0, float(n))
+        assert np.array_equal(r.cpu().numpy(), golden[name]["randoms"]), "minstd stream differs from the reference's"
+        c, info = ess.color(ctx, graphs[name])
+        want, it = oracle.color_jacobi(golden[name]["offsets"], golden[name]["indices"], golden[name]["randoms"])
+        assert np.array_equal(c.cpu().numpy(), want), name
+        assert info["iterations"] == it
+        assert oracle.color_errors(golden[name]["offsets"], golden[name]["indices"], c.cpu().numpy()) == 0
+    csr, g, (off, col, _) = s16
+    c, _ = ess.color(ctx, g)
+    assert np.array_equal(c.cpu().numpy(), oracle.color_jacobi(off, col)[0])
+
+
+# ------------------------------------------------------------------------------------------------ operators
+def _expected_advance(off, col, frontier, modulus):
+    kept, calls = [], np.zeros(max(col.size, 1), np.int64)
+    for v in frontier:
+        if v < 0:
+            continue
+        e = np.arange(off[v], off[v + 1], dtype=np.int64)
+        calls[e] += 1
+        keep = (v + col[e].astype(np.int64) + e) % modulus != 0
+        kept.append(col[e][keep])
+    return (np.sort(np.concatenate(kept)) if kept else np.zeros(0, np.int32)), calls
+
+
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+@pytest.mark.parametrize("lb", LBS)
+def test_advance_operator_multiset(ctx, lb, direction):
+    """Operator-level contract: op runs exactly once per (frontier item, edge) — holes skipped, duplicates
+    expanded twice — and the output is exactly the multiset of kept neighbours (order unspecified)."""
+    csr = gg.rmat_csr(11, symmetric=False, device="cuda")
+    csc = ess.transpose(csr)
+    g = ess.Graph(csr, csc=csc)
+    view = csr if direction == "forward" else csc
+    off, col, _ = view.host()
+    rng = np.random.default_rng(5)
+    cases = {
+        "random+holes+dups": np.concatenate([rng.integers(0, csr.n, 700), -np.ones(40, np.int64),
+                                             rng.integers(0, csr.n, 30).repeat(2)]),
+        "all": np.arange(csr.n),
+        "single-hub": np.array([int(np.argmax(np.diff(off)))]),
+        "only-holes": -np.ones(17, np.int64),
+        "empty": np.zeros(0, np.int64),
+    }
+    for label, f in cases.items():
+        f = f.astype(np.int32)
+        rng.shuffle(f)
+        out, calls = ess.advance_probe(ctx, g, torch.from_numpy(f).cuda(), lb=lb, direction=direction, modulus=3)
+        want, want_calls = _expected_advance(off, col, f, 3)
+        assert np.array_equal(np.sort(out.cpu().numpy()), want), (lb, direction, label)
+        assert np.array_equal(calls.cpu().numpy()[: col.size], want_calls[: col.size]), (lb, direction, label)
+
+
+@pytest.mark.parametrize("alg", ["predicated", "remove", "compact", "bypass"])
+def test_filter_operator(ctx, graphs, alg):
+    g = graphs["rmat_s10"]
+    rng = np.random.default_rng(9)
+    for size in (0, 1, 5, 1023, 1024, 1025, 40000):
+        items = rng.integers(0, g.n, size).astype(np.int32)
+        items[rng.random(size) < 0.1] = -1
+        keep = (items >= 0) & (items % 3 != 0)
+        out, calls = ess.filter_probe(ctx, g, torch.from_numpy(items).cuda(), alg=alg, modulus=3)
+        got = out.cpu().numpy()
+        if alg == "bypass":
+            assert np.array_equal(got, np.where(keep, items, -1)), size
+        else:
+            assert np.array_equal(got, items[keep]), f"{alg} must be a stable compaction (size {size})"
+        want_calls = np.bincount(items[items >= 0], minlength=g.n)
+        assert np.array_equal(calls.cpu().numpy()[: g.n], want_calls), "op exactly once per valid element"
+    items = torch.from_numpy(np.arange(5000, dtype=np.int32) % g.n).cuda()
+    out, _ = ess.filter_probe(ctx, g, items, alg="bypass", modulus=3, in_place=True)
+    want = np.arange(5000) % g.n
+    assert np.array_equal(out.cpu().numpy(), np.where(want % 3 != 0, want, -1))
+
+
+def test_frontier_sparse_dense_round_trip(ctx):
+    rng = np.random.default_rng(2)
+    for universe in (1, 31, 32, 33, 1000, 100003):
+        ids = np.unique(rng.integers(0, universe, universe // 3 + 1)).astype(np.int32)
+        noisy = np.concatenate([ids, ids[: len(ids) // 2], -np.ones(3, np.int32)])  # duplicates and holes
+        words, pop = ess.frontier_to_bitmap(ctx, torch.from_numpy(noisy).cuda(), universe)
+        assert pop == ids.size
+        bits = np.unpackbits(words.cpu().numpy().view(np.uint8), bitorder="little")[:universe]
+        assert np.array_equal(np.nonzero(bits)[0].astype(np.int32), ids)
+        back = ess.bitmap_to_frontier(ctx, words, universe)
+        assert np.array_equal(np.sort(back.cpu().numpy()), ids)
+
+
+def test_device_transpose_matches_host_transpose(ctx):
+    csr = gg.rmat_csr(12, symmetric=False, weights="hash", device="cuda")
+    t = ess.transpose(csr)
+    ref = gg.transpose_csr(csr)
+    assert torch.equal(t.offsets, ref.offsets)
+    key = lambda c: torch.sort(torch.repeat_interleave(torch.arange(c.n, device="cuda"), c.degrees().long()) * c.n
+                               + c.indices.long())[0]
+    assert torch.equal(key(t), key(ref))
+    # weights travel with their edge
+    order = lambda c: torch.argsort(torch.repeat_interleave(torch.arange(c.n, device="cuda"), c.degrees().long())
+                                    * c.n + c.indices.long())
+    assert torch.equal(t.values[order(t)], ref.values[order(ref)])
