@@ -40,7 +40,9 @@ class RunInfo(Structure):
 
     def as_dict(self):
         return {"enact_ms": float(self.enact_ms), "iterations": int(self.iterations),
-                "pull_steps": int(self.pull_steps), "push_steps": int(self.push_steps)}
+                "pull_steps": int(self.pull_steps), "push_steps": int(self.push_steps),
+                "pull_vertices": int(self.reserved[0]), "pull_edges": int(self.reserved[1]),
+                "push_vertices": int(self.reserved[2]), "push_edges": int(self.reserved[3])}
 
 
 _SIGNATURES = {
@@ -49,6 +51,8 @@ _SIGNATURES = {
     "ess_context_create": (c_int, [c_int, c_void_p, c_int, POINTER(c_void_p)]),
     "ess_context_destroy": (c_int, [c_void_p]),
     "ess_context_synchronize": (c_int, [c_void_p]),
+    "ess_profile_enable": (c_int, [c_void_p, c_int]),
+    "ess_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "ess_graph_create": (c_int, [c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                  c_void_p, POINTER(c_void_p)]),
     "ess_graph_destroy": (c_int, [c_void_p]),
@@ -127,6 +131,26 @@ class Context:
 
     def synchronize(self):
         _check(lib().ess_context_synchronize(self.handle), "ess_context_synchronize")
+
+    PROFILE_CLASSES = ("pull_step", "push_expand", "work_prepare", "dense_state", "filter")
+
+    def profile(self, enable: bool):
+        """Start (and reset) or stop per-kernel-class CUDA-event timing on this context's stream."""
+        _check(lib().ess_profile_enable(self.handle, int(enable)), "ess_profile_enable")
+
+    def profile_read(self):
+        """{class: (milliseconds, launches)} accumulated since profile(True)."""
+        ms = (ctypes.c_double * 8)()
+        cnt = (c_int64 * 8)()
+        _check(lib().ess_profile_read(self.handle, ms, cnt, 8), "ess_profile_read")
+        out = {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.PROFILE_CLASSES)}
+        self.kernel_launches = int(cnt[7])  # all operator kernels launched on this context so far
+        return out
+
+    def launches(self) -> int:
+        """Kernels the library has launched on this context since it was created."""
+        self.profile_read()
+        return self.kernel_launches
 
     def close(self):
         if getattr(self, "handle", None):

@@ -56,6 +56,30 @@ int ess_context_synchronize(ess_context_t ctx) {
   ESS_CATCH
 }
 
+int ess_profile_enable(ess_context_t ctx, int enable) {
+  ESS_TRY
+  auto& prof = ctx->single()->profiler();
+  prof.reset();
+  prof.enabled = enable != 0;
+  return 0;
+  ESS_CATCH
+}
+
+int ess_profile_read(ess_context_t ctx, double* ms_by_class, int64_t* launches_by_class, int n_classes) {
+  ESS_TRY
+  auto& prof = ctx->single()->profiler();
+  prof.collect();
+  for (int i = 0; i < n_classes && i < gcuda::profiler_t::n_classes; ++i) {
+    if (ms_by_class) ms_by_class[i] = prof.ms[i];
+    if (launches_by_class) launches_by_class[i] = prof.launches[i];
+  }
+  // last slot: every kernel the operators launched on this context since creation (always counted)
+  if (launches_by_class && n_classes >= gcuda::profiler_t::n_classes)
+    launches_by_class[gcuda::profiler_t::n_classes - 1] = prof.launches_total;
+  return 0;
+  ESS_CATCH
+}
+
 int ess_graph_create(int64_t n, int64_t m, int offset_bits, const void* d_row_offsets,
                      const int32_t* d_column_indices, const float* d_values, int symmetric,
                      const void* d_column_offsets, const int32_t* d_row_indices, const float* d_csc_values,

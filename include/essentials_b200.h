@@ -53,7 +53,8 @@ typedef struct ess_run_info {
   int32_t iterations; /* enactor_t::iteration at convergence */
   int32_t pull_steps; /* direction-optimised BFS: levels run bottom-up */
   int32_t push_steps; /* direction-optimised BFS: levels run top-down */
-  int64_t reserved[4];
+  int64_t reserved[4]; /* ess_bfs/OPTIMIZED work accounting: [0] vertices walked bottom-up, [1] in-edges read
+                          bottom-up (early exit counted), [2] vertices and [3] out-edges expanded top-down */
 } ess_run_info;
 
 ESS_API const char* ess_last_error(void);
@@ -66,6 +67,14 @@ ESS_API int ess_version(void);
 ESS_API int ess_context_create(int device, void* stream, int own_stream, ess_context_t* out);
 ESS_API int ess_context_destroy(ess_context_t ctx);
 ESS_API int ess_context_synchronize(ess_context_t ctx);
+
+/* Opt-in kernel timing with CUDA events on the context's stream (bench / roofline only; the reference's
+ * counterpart is nvbench's CUPTI collection, benchmarks/bfs_bench.cu:61-65). Classes: 0 pull step, 1 push
+ * expansion, 2 work preparation (scan/binning), 3 dense-state kernels (sparse<->dense, visited), 4 filters.
+ * ess_profile_enable resets the accumulators; ess_profile_read resolves pending events and copies
+ * accumulated milliseconds and launch counts (arrays of n_classes <= 8 entries). */
+ESS_API int ess_profile_enable(ess_context_t ctx, int enable);
+ESS_API int ess_profile_read(ess_context_t ctx, double* ms_by_class, int64_t* launches_by_class, int n_classes);
 
 /* graph::build::from_csr<device, csr[|csc]> (include/gunrock/graph/build.hxx:21-36).
  * d_row_offsets: (n+1) x int32 or int64 (offset_bits = 32|64); d_column_indices: m x int32;

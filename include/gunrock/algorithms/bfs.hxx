@@ -60,7 +60,11 @@ struct enactor_t : gunrock::enactor_t<problem_t> {
 
   enactor_t(problem_t* _problem, std::shared_ptr<gcuda::multi_context_t> _context,
             enactor_properties_t _properties = enactor_properties_t())
-      : base_t(_problem, _context, _properties) {}
+      : base_t(_problem, _context, _properties) {
+    if constexpr (direction == operators::advance_direction_t::optimized)  // bitmaps sized outside the timed loop
+      this->direction.allocate(std::size_t(_problem->get_graph().get_number_of_vertices()),
+                               _context->get_context(0)->stream());
+  }
 
   void prepare_frontier(frontier_t* f, gcuda::multi_context_t& context) override {
     f->push_back(this->get_problem()->param.single_source);
@@ -87,7 +91,8 @@ float run(graph_t& G, typename graph_t::vertex_type& single_source, typename gra
           typename graph_t::vertex_type* predecessors,
           std::shared_ptr<gcuda::multi_context_t> context =
               std::shared_ptr<gcuda::multi_context_t>(new gcuda::multi_context_t(0)),
-          enactor_properties_t properties = enactor_properties_t(), int* pull_steps = nullptr, int* iterations = nullptr) {
+          enactor_properties_t properties = enactor_properties_t(), int* pull_steps = nullptr, int* iterations = nullptr,
+          long long* work_stats = nullptr) {
   using vertex_t = typename graph_t::vertex_type;
   using param_type = param_t<vertex_t>;
   using result_type = result_t<vertex_t>;
@@ -103,6 +108,12 @@ float run(graph_t& G, typename graph_t::vertex_type& single_source, typename gra
   float ms = enactor.enact();
   if (pull_steps) *pull_steps = enactor.direction.pull_steps;
   if (iterations) *iterations = enactor.iteration;
+  if (work_stats) {  // [0] pull vertices walked, [1] pull in-edges read, [2] push vertices, [3] push edges
+    work_stats[0] = enactor.direction.pull_vertices_scanned;
+    work_stats[1] = enactor.direction.pull_edges_inspected;
+    work_stats[2] = enactor.direction.push_vertices_expanded;
+    work_stats[3] = enactor.direction.push_edges_expanded;
+  }
   return ms;
 }
 

@@ -53,14 +53,17 @@ inline unsigned stream_grid(gcuda::standard_context_t& ctx, std::size_t n) {
 template <typename T>
 void fill(gcuda::standard_context_t& ctx, T* out, std::size_t n, T value) {
   if (n) kernels::fill_kernel<<<stream_grid(ctx, n), 256, 0, ctx.stream()>>>(out, n, value);
+  ctx.profiler().launches_total += n ? 1 : 0;
 }
 template <typename T>
 void copy(gcuda::standard_context_t& ctx, const T* in, T* out, std::size_t n) {
   if (n) kernels::copy_kernel<<<stream_grid(ctx, n), 256, 0, ctx.stream()>>>(in, out, n);
+  ctx.profiler().launches_total += n ? 1 : 0;
 }
 template <typename T>
 void set_one(gcuda::standard_context_t& ctx, T* at, T value) {
   kernels::fill_kernel<<<1, 32, 0, ctx.stream()>>>(at, std::size_t(1), value);
+  ctx.profiler().launches_total += 1;
 }
 
 }  // namespace b200

@@ -92,6 +92,71 @@ struct scratch_t {
   }
 };
 
+/**
+ * @brief Opt-in per-kernel-class timing with CUDA events on the launching stream (bench/roofline use).
+ * Disabled by default: begin()/end() are then a single predictable branch. Events are recorded
+ * asynchronously and only resolved in collect(), so an instrumented run does not add synchronisations.
+ */
+struct profiler_t {
+  enum kernel_class : int {
+    pull_step = 0,     // bottom-up level (pull.cuh)
+    push_expand = 1,   // thread/block/merge-path/bucket expansion kernels
+    work_prepare = 2,  // degree scan / binning / Σdeg
+    dense_state = 3,   // sparse<->dense conversion, visited init, frontier degree sum
+    filter_op = 4,     // filter kernels
+    n_classes = 8
+  };
+  struct span_t {
+    int cls;
+    cudaEvent_t a, b;
+  };
+  bool enabled = false;
+  std::vector<span_t> spans;
+  std::size_t used = 0;
+  double ms[n_classes] = {0};
+  long long launches[n_classes] = {0};
+  long long launches_total = 0;  ///< kernels launched by the operators on this context (always counted)
+
+  ~profiler_t() {
+    for (auto& sp : spans) {
+      cudaEventDestroy(sp.a);
+      cudaEventDestroy(sp.b);
+    }
+  }
+  void begin(int cls, cudaStream_t stream) {
+    if (!enabled) return;
+    if (used == spans.size()) {
+      span_t sp{cls, nullptr, nullptr};
+      cudaEventCreate(&sp.a);
+      cudaEventCreate(&sp.b);
+      spans.push_back(sp);
+    }
+    spans[used].cls = cls;
+    cudaEventRecord(spans[used].a, stream);
+  }
+  void end(cudaStream_t stream, int kernels = 1) {
+    launches_total += kernels;
+    if (!enabled) return;
+    cudaEventRecord(spans[used].b, stream);
+    ++used;
+  }
+  /// Resolve all recorded spans into ms[] / launches[] (synchronises on the last event).
+  void collect() {
+    for (std::size_t i = 0; i < used; ++i) {
+      float t = 0.f;
+      cudaEventSynchronize(spans[i].b);
+      cudaEventElapsedTime(&t, spans[i].a, spans[i].b);
+      ms[spans[i].cls] += double(t);
+      launches[spans[i].cls] += 1;
+    }
+    used = 0;
+  }
+  void reset() {
+    collect();
+    for (int i = 0; i < n_classes; ++i) ms[i] = 0, launches[i] = 0;
+  }
+};
+
 /// Bump allocator over scratch_t::temp(): lay out all temporaries of one operator call, then carve.
 struct arena_layout_t {
   std::size_t bytes = 0;
@@ -142,6 +207,7 @@ class standard_context_t {
     _scratch.init();
     return _scratch;
   }
+  profiler_t& profiler() { return _profiler; }
 
  private:
   void init() {
@@ -157,6 +223,7 @@ class standard_context_t {
   event_t _event{};
   util::timer_t _timer;
   scratch_t _scratch;
+  profiler_t _profiler;
 };
 
 inline void standard_context_t::print_properties() {

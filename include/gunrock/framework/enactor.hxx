@@ -59,6 +59,17 @@ struct direction_state_t {
   long long frontier_vertices = 0;
   long long previous_frontier_vertices = 0;
   int pull_steps = 0, push_steps = 0;  ///< statistics for the harness
+  long long pull_vertices_scanned = 0;  ///< unvisited vertices walked by bottom-up levels
+  long long pull_edges_inspected = 0;   ///< in-edges read by bottom-up levels (early exit counted)
+  long long push_edges_expanded = 0;    ///< out-edges expanded by top-down levels
+  long long push_vertices_expanded = 0; ///< frontier vertices expanded by top-down levels
+  /// Size the three bitmaps for n vertices (idempotent; call before enact() to keep it out of the timed loop).
+  void allocate(std::size_t n, gcuda::stream_t stream = 0) {
+    if (visited.get_universe() == n) return;
+    visited.resize(n, stream);
+    dense[0].resize(n, stream);
+    dense[1].resize(n, stream);
+  }
   void reset() {
     initialised = false;
     frontier_is_dense = false;
@@ -66,6 +77,7 @@ struct direction_state_t {
     dense_selector = 0;
     frontier_edges = unexplored_edges = frontier_vertices = previous_frontier_vertices = 0;
     pull_steps = push_steps = 0;
+    pull_vertices_scanned = pull_edges_inspected = push_edges_expanded = push_vertices_expanded = 0;
   }
 };
 
@@ -103,6 +115,7 @@ struct enactor_t {
         iteration(0) {
     if (!properties.self_manage_frontiers) {
       auto g = problem->get_graph();
+      scanned_work_domain.resize(std::size_t(g.get_number_of_vertices()) + 1);  // as the reference (:168)
       std::size_t initial = properties.initial_frontier_capacity ? properties.initial_frontier_capacity
                                                                  : std::size_t(g.get_number_of_vertices());
       for (auto& buffer : frontiers) {

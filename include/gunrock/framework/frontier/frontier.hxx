@@ -123,9 +123,7 @@ struct frontier_storage_t {
   frontier_storage_t() = default;
   frontier_storage_t(const frontier_storage_t&) = delete;
   frontier_storage_t& operator=(const frontier_storage_t&) = delete;
-  ~frontier_storage_t() {
-    if (ptr) cudaFree(ptr);
-  }
+  ~frontier_storage_t() { memory::free(ptr); }
   void grow(std::size_t n, std::size_t live) {
     if (n <= cap) return;
     type_t* fresh = memory::allocate<type_t>(n * sizeof(type_t));
@@ -133,7 +131,7 @@ struct frontier_storage_t {
       if (live)
         error::throw_if_exception(cudaMemcpy(fresh, ptr, live * sizeof(type_t), cudaMemcpyDeviceToDevice),
                                   "frontier grow");
-      cudaFree(ptr);
+      memory::free(ptr);
     }
     ptr = fresh;
     cap = n;
@@ -328,14 +326,13 @@ class bitmap_frontier_t {
   /// Number of active ids; runs a popcount kernel only if the map changed since the last query.
   std::size_t get_number_of_elements(gcuda::stream_t stream = 0) {
     if (dirty) {
-      b200::counter_t* d_total = nullptr;
-      cudaMalloc(&d_total, sizeof(b200::counter_t));
+      b200::counter_t* d_total = memory::allocate<b200::counter_t>(sizeof(b200::counter_t));
       cudaMemsetAsync(d_total, 0, sizeof(b200::counter_t), stream);
       kernels::popcount_kernel<<<148 * 4, 256, 0, stream>>>(raw_ptr, words(), d_total);
       b200::counter_t h = 0;
       cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, stream);
       cudaStreamSynchronize(stream);
-      cudaFree(d_total);
+      memory::free(d_total);
       cached_count = std::size_t(h);
       dirty = false;
     }

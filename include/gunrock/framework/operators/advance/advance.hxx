@@ -79,10 +79,16 @@ void grow_output(frontier_t* output, std::size_t needed) {
  * test-and-set policy (direction-optimised callers); null keeps reference semantics.
  * `input_size_on_device`/`next_edges` are used by the optimised path only.
  */
+struct no_epilogue_t {
+  template <typename... args_t>
+  void operator()(args_t&&...) const {}
+};
+
 template <load_balance_t lb, bool use_csc, advance_io_type_t input_type, advance_io_type_t output_type, visit_t policy,
-          typename graph_t, typename operator_t, typename frontier_t, typename work_tiles_t>
+          typename graph_t, typename operator_t, typename frontier_t, typename work_tiles_t,
+          typename epilogue_t = no_epilogue_t>
 void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, work_tiles_t& segments,
-            gcuda::standard_context_t& ctx, unsigned* visited) {
+            gcuda::standard_context_t& ctx, unsigned* visited, epilogue_t epilogue = epilogue_t()) {
   using vertex_t = typename graph_t::vertex_type;
   using edge_t = typename graph_t::edge_type;
   constexpr bool graph_input = input_type == advance_io_type_t::graph;
@@ -99,6 +105,8 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
     return;
   }
   auto& scratch = ctx.scratch();
+  auto& prof = ctx.profiler();
+  using gcuda::profiler_t;
   auto stream = ctx.stream();
   const vertex_t* in = graph_input ? nullptr : input->data();
   const std::size_t prep_tiles = (nf + kernels::cta_threads * kernels::prep_items - 1) /
@@ -114,9 +122,13 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
     if constexpr (lb == load_balance_t::thread_mapped || lb == load_balance_t::block_mapped) {
       const long long maxdeg = max_degree(ctx, A.offsets, A.n);
       const bool guard = has_output && (long double)(nf) * (long double)(maxdeg) > (long double)(capacity);
-      if (guard)
+      if (guard) {
+        prof.begin(profiler_t::work_prepare, stream);
         kernels::degree_sum_kernel<graph_input><<<gcuda::persistent_grid(ctx, item_ctas, 8), 256, 0, stream>>>(
             A.offsets, in, nf, C);
+        prof.end(stream);
+      }
+      prof.begin(profiler_t::push_expand, stream);
       if constexpr (lb == load_balance_t::thread_mapped) {
         const unsigned grid = gcuda::persistent_grid(ctx, item_ctas, 8);
         if (guard)
@@ -142,8 +154,10 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
           // (the hub kernel's capacity guard reads Σdeg, which is 0 = "fits" when it was not needed)
           kernels::big_list_kernel<has_output, policy><<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(
               A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
+          prof.launches_total += 1;
         }
       }
+      prof.end(stream);
     } else if constexpr (lb == load_balance_t::merge_path || lb == load_balance_t::merge_path_v2) {
       if (segments.size() < nf + 1) segments.resize(nf + 1);
       gcuda::arena_layout_t layout;
@@ -155,12 +169,16 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
       auto* work_beg = reinterpret_cast<edge_t*>(base + at_beg);
       auto* state = reinterpret_cast<b200::tile_word_t*>(base + at_state);
       edge_t* work_seg = raw_of(segments.data());
+      prof.begin(profiler_t::work_prepare, stream);
       cudaMemsetAsync(state, 0, 2 * prep_tiles * sizeof(b200::tile_word_t), stream);
       kernels::prepare_work_kernel<graph_input><<<gcuda::persistent_grid(ctx, prep_tiles, 6), 256, 0, stream>>>(
           A.offsets, in, nf, work_src, work_beg, work_seg, state, state + prep_tiles, C);
+      prof.end(stream);
+      prof.begin(profiler_t::push_expand, stream);
       kernels::merge_path_kernel<has_output, policy>
           <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(A, op, work_src, work_beg, work_seg,
                                                                                 out, C, capacity, visited);
+      prof.end(stream);
     } else if constexpr (lb == load_balance_t::bucketing) {
       gcuda::arena_layout_t layout;
       const std::size_t at_small = layout.add(nf * sizeof(vertex_t));
@@ -170,8 +188,11 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
       auto* small_list = reinterpret_cast<vertex_t*>(base + at_small);
       auto* warp_list = reinterpret_cast<vertex_t*>(base + at_warp);
       auto* big_list = reinterpret_cast<vertex_t*>(base + at_big);
+      prof.begin(profiler_t::work_prepare, stream);
       kernels::bin_by_degree_kernel<graph_input><<<gcuda::persistent_grid(ctx, item_ctas, 8), 256, 0, stream>>>(
           A.offsets, in, nf, small_list, warp_list, big_list, C);
+      prof.end(stream);
+      prof.begin(profiler_t::push_expand, stream);
       kernels::thread_mapped_kernel<false, has_output, true, policy>
           <<<gcuda::persistent_grid(ctx, item_ctas, 8), 256, 0, stream>>>(A, op, small_list, 0, C + scratch_t::aux0, out,
                                                                         C, capacity, visited);
@@ -180,9 +201,11 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
                                                                             capacity, visited);
       kernels::big_list_kernel<has_output, policy><<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(
           A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
+      prof.end(stream, 3);
     } else {
       error::throw_if_exception(cudaErrorUnknown, "Advance type not supported.");
     }
+    epilogue(C, out);  // extra kernels that consume the device-side output count before the one sync
     error::check_last("advance launch");
     scratch.fetch(stream);
     if constexpr (has_output) {
@@ -209,6 +232,8 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
                 "direction-optimised advance maps a vertex frontier to a vertex frontier");
   auto& D = E->direction;
   auto& scratch = ctx.scratch();
+  auto& prof = ctx.profiler();
+  using gcuda::profiler_t;
   auto stream = ctx.stream();
   const auto out_adj = graph::adjacency_of<false>(G);
   const auto in_adj = graph::adjacency_of<true>(G);
@@ -217,16 +242,16 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
   auto* output = E->get_output_frontier();
 
   if (!D.initialised) {
-    D.visited.resize(std::size_t(n), stream);
-    D.dense[0].resize(std::size_t(n), stream);
-    D.dense[1].resize(std::size_t(n), stream);
+    D.allocate(std::size_t(n), stream);
     const std::size_t nf = input->get_number_of_elements();
     scratch.zero(stream);
+    prof.begin(profiler_t::dense_state, stream);
     kernels::init_visited_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 8), 256, 0, stream>>>(
         in_adj.offsets, n, D.visited.data());
     if (nf)
       kernels::mark_frontier_kernel<<<gcuda::persistent_grid(ctx, (nf + 255) / 256, 8), 256, 0, stream>>>(
           out_adj.offsets, input->data(), nf, nullptr, D.visited.data(), scratch.d);
+    prof.end(stream);
     scratch.fetch(stream);
     D.frontier_edges = (long long)scratch.h[scratch_t::aux2];
     D.unexplored_edges = (long long)out_adj.m - D.frontier_edges;
@@ -251,39 +276,50 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
   long long next_vertices = 0, next_edges = 0;
   if (D.pulling) {
     if (!D.frontier_is_dense) {  // sparse -> dense
+      prof.begin(profiler_t::dense_state, stream);
       frontier::convert(*input, D.dense[D.dense_selector], stream);
+      prof.end(stream);
       D.frontier_is_dense = true;
     }
     auto& cur = D.dense[D.dense_selector];
     auto& nxt = D.dense[D.dense_selector ^ 1];
     scratch.zero(stream);
+    prof.begin(profiler_t::pull_step, stream);
     kernels::pull_step_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 8), 256, 0, stream>>>(
         in_adj, op, cur.data(), nxt.data(), D.visited.data(), scratch.d);
+    prof.end(stream);
     error::check_last("pull step");
     scratch.fetch(stream);
     next_vertices = (long long)scratch.h[scratch_t::out_count];
     next_edges = (long long)scratch.h[scratch_t::aux2];
+    D.pull_vertices_scanned += (long long)scratch.h[scratch_t::aux0];
+    D.pull_edges_inspected += (long long)scratch.h[scratch_t::aux1];
     D.dense_selector ^= 1;
     D.dense[D.dense_selector].set_number_of_elements(std::size_t(next_vertices));
     output->set_number_of_elements(std::size_t(next_vertices));  // contents live in the dense map
     ++D.pull_steps;
   } else {
     if (D.frontier_is_dense) {  // dense -> sparse
+      prof.begin(profiler_t::dense_state, stream);
       frontier::convert(D.dense[D.dense_selector], *input, ctx);
+      prof.end(stream);
       D.frontier_is_dense = false;
     }
+    D.push_vertices_expanded += D.frontier_vertices;
+    D.push_edges_expanded += D.frontier_edges;
     grow_output(output, std::size_t(n));
+    // Σdeg of the new frontier (Beamer's m_f) is accumulated by a follow-up kernel that reads the output
+    // length from the device counter, so the whole level still costs a single host synchronisation.
+    auto degree_sum_of_output = [&](counter_t* C, vertex_t* out) {
+      prof.begin(profiler_t::dense_state, stream);
+      kernels::mark_frontier_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 2), 256, 0, stream>>>(
+          out_adj.offsets, out, std::size_t(0), C + scratch_t::out_count, (unsigned*)nullptr, C);
+      prof.end(stream);
+    };
     expand<lb, false, input_type, output_type, visit_t::test_and_set>(G, op, input, output, E->scanned_work_domain, ctx,
-                                                                     D.visited.data());
+                                                                     D.visited.data(), degree_sum_of_output);
     next_vertices = (long long)output->get_number_of_elements();
-    if (next_vertices) {
-      scratch.zero(stream);
-      kernels::mark_frontier_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(next_vertices) + 255) / 256, 8), 256, 0,
-                                      stream>>>(out_adj.offsets, output->data(), std::size_t(next_vertices), nullptr,
-                                                (unsigned*)nullptr, scratch.d);
-      scratch.fetch(stream);
-      next_edges = (long long)scratch.h[scratch_t::aux2];
-    }
+    next_edges = next_vertices ? (long long)scratch.h[scratch_t::aux2] : 0;
     ++D.push_steps;
   }
   D.previous_frontier_vertices = D.frontier_vertices;

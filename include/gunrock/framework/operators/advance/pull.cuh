@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256)
 }
 
 /**
- * @brief One bottom-up level. counters[out_count] += |next frontier|, counters[aux2] += Σdeg(next frontier).
+ * @brief One bottom-up level. counters[out_count] += |next frontier|, counters[aux2] += Σdeg(next frontier),
+ * counters[aux0] += unvisited vertices walked, counters[aux1] += in-edges read (work accounting).
  * `A` is the CSC adjacency (for a symmetric graph it aliases the CSR arrays).
  */
 template <typename vertex_t, typename edge_t, typename weight_t, typename operator_t>
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(256)
   const unsigned lane = b200::lane_id();
   const std::size_t n_words = (std::size_t(A.n) + 31) / 32;
   const std::size_t warps = (std::size_t(gridDim.x) * blockDim.x) >> 5;
-  counter_t found_vertices = 0, found_edges = 0;
+  counter_t found_vertices = 0, found_edges = 0, scanned = 0, inspected = 0;
   for (std::size_t w = (std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
     const unsigned seen = visited[w];
     bool found = false;
@@ -85,7 +86,9 @@ __global__ void __launch_bounds__(256)
       const vertex_t v = vertex_t(w * 32 + lane);
       const edge_t beg = A.offsets[v], end = A.offsets[v + 1];
       deg = end - beg;
+      ++scanned;
       for (edge_t e = beg; e < end; ++e) {
+        ++inspected;
         const vertex_t u = __ldg(A.indices + e);
         if ((__ldg(frontier_bits + (unsigned(u) >> 5)) >> (unsigned(u) & 31u)) & 1u) {
           weight_t weight = A.values ? __ldg(A.values + e) : weight_t(1);
@@ -107,9 +110,13 @@ __global__ void __launch_bounds__(256)
     if (found) found_edges += counter_t(deg);
   }
   found_edges = b200::warp_sum(found_edges);
+  scanned = b200::warp_sum(scanned);
+  inspected = b200::warp_sum(inspected);
   if (lane == 0) {
     if (found_vertices) atomicAdd(counters + scratch_t::out_count, found_vertices);
     if (found_edges) atomicAdd(counters + scratch_t::aux2, found_edges);
+    if (scanned) atomicAdd(counters + scratch_t::aux0, scanned);      // unvisited vertices walked
+    if (inspected) atomicAdd(counters + scratch_t::aux1, inspected);  // in-edges actually read
   }
 }
 

@@ -204,8 +204,10 @@ void select(graph_t&, operator_t op, frontier_t* input, frontier_t* output, gcud
   auto* state = reinterpret_cast<b200::tile_word_t*>(scratch.temp(n_tiles * sizeof(b200::tile_word_t)));
   scratch.zero(stream);
   cudaMemsetAsync(state, 0, n_tiles * sizeof(b200::tile_word_t), stream);
+  ctx.profiler().begin(gcuda::profiler_t::filter_op, stream);
   kernels::select_kernel<type_t><<<gcuda::persistent_grid(ctx, n_tiles, 6), 256, 0, stream>>>(
       input->data(), count, output->data(), op, state, scratch.d);
+  ctx.profiler().end(stream);
   error::check_last("filter select");
   scratch.fetch(stream);
   output->set_number_of_elements(std::size_t(scratch.h[scratch_t::out_count]));
@@ -232,17 +234,21 @@ void compact(graph_t&, operator_t op, frontier_t* input, frontier_t* output, gcu
   auto* tile_offsets = reinterpret_cast<unsigned long long*>(base + at_offsets);
   scratch.zero(stream);
   const unsigned grid = gcuda::persistent_grid(ctx, n_tiles, 6);
+  ctx.profiler().begin(gcuda::profiler_t::filter_op, stream);
   kernels::compact_upsweep_kernel<type_t><<<grid, 256, 0, stream>>>(input->data(), count, op, base + at_bits,
                                                                     tile_counts, scratch.d);
   kernels::compact_scan_tiles_kernel<<<1, 1024, 0, stream>>>(tile_counts, tile_offsets, int(n_tiles));
+  ctx.profiler().end(stream, 2);
   error::check_last("filter compact upsweep");
   scratch.fetch(stream);  // exact size known here: allocate exactly, then scatter
   const std::size_t kept = std::size_t(scratch.h[scratch_t::out_count]);
   ensure(output, kept);
   output->set_number_of_elements(kept);
   if (kept) {
+    ctx.profiler().begin(gcuda::profiler_t::filter_op, stream);
     kernels::compact_downsweep_kernel<type_t><<<grid, 256, 0, stream>>>(input->data(), count, output->data(),
                                                                         base + at_bits, tile_offsets);
+    ctx.profiler().end(stream);
     error::check_last("filter compact downsweep");
     ctx.synchronize();
   }
@@ -256,8 +262,10 @@ void bypass(graph_t&, operator_t op, frontier_t* input, frontier_t* output, gcud
   output->set_number_of_elements(count);
   if (!count) return;
   const std::size_t ctas = (count + kernels::per_tile - 1) / kernels::per_tile;
+  ctx.profiler().begin(gcuda::profiler_t::filter_op, ctx.stream());
   kernels::bypass_kernel<type_t><<<gcuda::persistent_grid(ctx, ctas, 8), 256, 0, ctx.stream()>>>(
       input->data(), count, output->data(), op);
+  ctx.profiler().end(ctx.stream());
   error::check_last("filter bypass");
   ctx.synchronize();
 }

@@ -8,7 +8,11 @@
 
 #include <cstddef>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <utility>
+#include <vector>
 #include <cuda_runtime_api.h>
 #include <gunrock/error.hxx>
 
@@ -17,19 +21,111 @@ namespace memory {
 
 enum memory_space_t { device, host };
 
+/**
+ * @brief Process-wide caching allocator for device memory. Every enactor run needs the same handful of
+ * buffers (two frontiers, work offsets, bitmaps, per-vertex state); cudaMalloc/cudaFree cost 0.1-1 ms each
+ * and cudaFree synchronises the device, which is more than a whole BFS on B200. Blocks are returned to a
+ * per-(device, rounded size) free list instead and handed out again on the next run, so after the first
+ * run of a given shape no call reaches the driver. Safe because every operator synchronises its stream
+ * before returning: a block is only released by host code after the GPU is done with it.
+ * The cache is intentionally never destroyed at exit (the CUDA runtime may already be gone).
+ */
+class device_pool_t {
+ public:
+  static device_pool_t& instance() {
+    static device_pool_t* pool = new device_pool_t;
+    return *pool;
+  }
+  void* acquire(std::size_t bytes) {
+    if (!bytes) return nullptr;
+    const std::size_t rounded = round_up(bytes);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      auto it = cached.find({dev, rounded});
+      if (it != cached.end() && !it->second.empty()) {
+        void* p = it->second.back();
+        it->second.pop_back();
+        cached_bytes -= rounded;
+        live[p] = {dev, rounded};
+        return p;
+      }
+    }
+    void* p = nullptr;
+    cudaError_t st = cudaMalloc(&p, rounded);
+    if (st != cudaSuccess) {  // out of memory: give the cache back to the driver and retry once
+      cudaGetLastError();
+      trim();
+      st = cudaMalloc(&p, rounded);
+    }
+    error::throw_if_exception(st, "memory::allocate");
+    std::lock_guard<std::mutex> lock(mu);
+    live[p] = {dev, rounded};
+    return p;
+  }
+  void release(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = live.find(p);
+    if (it == live.end()) {  // not ours (allocated before the pool existed): plain free
+      cudaFree(p);
+      return;
+    }
+    cached[it->second].push_back(p);
+    cached_bytes += it->second.second;
+    live.erase(it);
+  }
+  /// Return every cached (unused) block to the driver.
+  void trim() {
+    std::lock_guard<std::mutex> lock(mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : cached) {
+      cudaSetDevice(kv.first.first);
+      for (void* p : kv.second) cudaFree(p);
+      kv.second.clear();
+    }
+    cudaSetDevice(cur);
+    cached_bytes = 0;
+  }
+  std::size_t bytes_cached() const { return cached_bytes; }
+
+ private:
+  static std::size_t round_up(std::size_t b) {
+    if (b <= (std::size_t(1) << 20)) {
+      std::size_t r = 256;
+      while (r < b) r <<= 1;
+      return r;
+    }
+    const std::size_t grain = std::size_t(2) << 20;
+    return (b + grain - 1) / grain * grain;
+  }
+  std::mutex mu;
+  std::map<std::pair<int, std::size_t>, std::vector<void*>> cached;
+  std::unordered_map<void*, std::pair<int, std::size_t>> live;
+  std::size_t cached_bytes = 0;
+};
+
 template <typename type_t>
 inline type_t* allocate(std::size_t bytes, memory_space_t space = memory_space_t::device) {
   void* p = nullptr;
-  if (bytes)
-    error::throw_if_exception(space == device ? cudaMalloc(&p, bytes) : cudaMallocHost(&p, bytes),
-                              "memory::allocate");
+  if (bytes) {
+    if (space == device)
+      p = device_pool_t::instance().acquire(bytes);
+    else
+      error::throw_if_exception(cudaMallocHost(&p, bytes), "memory::allocate");
+  }
   return static_cast<type_t*>(p);
 }
 
 template <typename type_t>
 inline void free(type_t* p, memory_space_t space = memory_space_t::device) {
-  if (p)
-    error::throw_if_exception(space == device ? cudaFree((void*)p) : cudaFreeHost((void*)p), "memory::free");
+  if (!p) return;
+  if (space == device)
+    device_pool_t::instance().release((void*)p);
+  else
+    error::throw_if_exception(cudaFreeHost((void*)p), "memory::free");
 }
 
 template <typename type_t>
@@ -53,10 +149,7 @@ class device_array_t {
     swap(o);
     return *this;
   }
-  ~device_array_t() {
-    if (ptr)
-      cudaFree(ptr);
-  }
+  ~device_array_t() { memory::free(ptr); }
 
   void swap(device_array_t& o) noexcept {
     std::swap(ptr, o.ptr);
@@ -72,7 +165,7 @@ class device_array_t {
       if (keep && count)
         error::throw_if_exception(cudaMemcpy(fresh, ptr, count * sizeof(type_t), cudaMemcpyDeviceToDevice),
                                   "device_array_t::reserve");
-      cudaFree(ptr);
+      memory::free(ptr);
     }
     ptr = fresh;
     cap = n;
