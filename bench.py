@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scale", type=int, default=24, help="Kronecker scale (BASELINE config 2: 24)")
+    ap.add_argument("--scale", type=int, default=0,
+                    help="Kronecker scale; default 24 (BASELINE config 2) at every GPU count = strong scaling")
     ap.add_argument("--edge-factor", type=int, default=16)
     ap.add_argument("--lb", default="merge_path")
     ap.add_argument("--direction", default="optimized")
@@ -119,9 +120,9 @@ def run_reference(args, rank, world):
     from essentials_b200 import graphgen as gg
     steps_total = args.steps + args.warmup
     # bounded sample: the largest Kronecker scale <= the configured one whose (K+W) CPU traversals fit the budget
-    # (bfs_cpu sustains roughly 0.03 GTEPS on one core; measured figure is what gets printed)
+    # (bfs_cpu sustains roughly 0.08-0.12 GTEPS on one core incl. its array copies; measured figure is what gets printed)
     scale = args.scale
-    while scale > 16 and (args.edge_factor << scale) * 2 * steps_total / 30e6 > args.cpu_budget_s:
+    while scale > 16 and (args.edge_factor << scale) * 2 * steps_total / 80e6 > args.cpu_budget_s:
         scale -= 1
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     csr = gg.rmat_csr(scale, args.edge_factor, device=dev)
@@ -173,9 +174,11 @@ def run_b200(args, rank, world, local_rank):
 
     if distributed:
         from essentials_b200 import dist as edist
-        runner = edist.PartitionedBFS(args.scale, args.edge_factor, rank, world, dev, stream)
+        runner = edist.build_partitioned(args.scale, args.edge_factor, rank, world, dev, stream)
+        stream.synchronize()
         n, m, offset_bits = runner.n_global, runner.m_global, runner.offset_bits
-        srcs = runner.pick_sources(K + W)
+        with torch.cuda.stream(stream):
+            srcs = runner.pick_sources(K + W)
     else:
         with torch.cuda.stream(stream):
             csr = gg.rmat_csr(args.scale, args.edge_factor, device=dev)
@@ -208,7 +211,7 @@ def run_b200(args, rank, world, local_rank):
     verts = sum(work[s][0] for s in timed)
 
     # ---- timed region: K steps, device events on the launching stream, barrier + sync on both sides ----
-    launches0 = 0 if distributed else ctx.launches()
+    launches0 = runner.backend.launches() if distributed else ctx.launches()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if distributed:
         dist.barrier()
@@ -229,7 +232,7 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if sampler else None
-    launches = (runner.launches() if distributed else ctx.launches()) - launches0
+    launches = (runner.backend.launches() if distributed else ctx.launches()) - launches0
     value = edges / (ms * 1e-3) / 1e9
 
     out = {
@@ -324,8 +327,42 @@ def run_b200(args, rank, world, local_rank):
             if not same:
                 out["parity_error"] = "GPU depths differ from the CPU reference"
     else:
-        out["e2e"] = runner.e2e(timed, edges)
-        out["roofline"] = runner.roofline(peak_gbs, peak_src)
+        # ---- multi-GPU: NVLink-side accounting + e2e with this rank's partition in host memory ---------
+        out["config"]["exchange"] = ("per level: all_to_all of candidate bitmap slices (top-down levels only) + one "
+                                     "all_gather of the next-frontier slice and Beamer counters; NCCL over NVLink")
+        out["config"]["levels"] = runner.levels
+        out["config"]["pull_levels"] = runner.pull_levels
+        nv_bytes = runner.bytes_exchanged  # received per rank in the last BFS
+        out["roofline"] = {"bound": "hbm", "kernel": "partitioned level kernels", "achieved": None, "peak": peak_gbs,
+                           "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                           "nvlink_bytes_received_per_rank_per_bfs": nv_bytes,
+                           "nvlink_time_floor_ms": nv_bytes / 770e9 * 1e3,
+                           "note": "multi-GPU steps are latency-bound by the per-level exchange; single-GPU run "
+                                   "carries the kernel roofline"}
+        if not args.no_e2e:
+            csr = runner.csr
+            h_off, h_col = csr.offsets.cpu().pin_memory(), csr.indices.cpu().pin_memory()
+            h_depth = torch.empty(runner.per, dtype=torch.int32).pin_memory()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            torch.cuda.synchronize()
+            with torch.cuda.stream(stream):
+                f0.record(stream)
+                for s in timed:
+                    csr.offsets.copy_(h_off, non_blocking=True)
+                    csr.indices.copy_(h_col, non_blocking=True)
+                    one_bfs(s)
+                    h_depth.copy_(runner.depth_local, non_blocking=True)
+                f1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([f0.elapsed_time(f1)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+            out["e2e"] = {"value": edges / (ems * 1e-3) / 1e9, "unit": "GTEPS",
+                          "h2d_bytes_per_step": int(h_off.numel() * h_off.element_size() + h_col.numel() * 4 + 4) * world,
+                          "d2h_bytes_per_step": int(n * 4), "ms_per_step": ems / K,
+                          "what": "per step and rank: this rank's CSR partition H2D from pinned memory, the BFS, "
+                                  "the owned depth slice D2H (bytes summed over ranks)"}
 
     if rank == 0:
         print(json.dumps(out), flush=True)
@@ -333,6 +370,8 @@ def run_b200(args, rank, world, local_rank):
 
 def main():
     args = parse()
+    if args.scale <= 0:
+        args.scale = 24
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -1,0 +1,225 @@
+"""Multi-GPU BFS: 1-D vertex partition, one process per GPU, per-level frontier exchange with torch.distributed.
+
+The reference has no multi-GPU path (its operators throw when ``context.size() != 1``,
+include/gunrock/framework/operators/advance/advance.hxx:125-128).  This module is the
+extension BASELINE.json asks for: rank r owns the contiguous vertex range [r*n/P, (r+1)*n/P) — its CSR rows
+with GLOBAL column ids and its slice of the depth array — and the frontier / visited sets are replicated
+1-bit-per-vertex maps (32 MiB at scale-28), so an exchange is a fixed-size collective:
+
+  top-down level   local advance ORs unvisited neighbours into a global-length candidate map
+                   -> all_to_all of the P candidate slices, owner ORs them        (n/8 bytes sent per rank)
+  bottom-up level  owner walks the in-edges of its unvisited vertices against the replicated frontier map
+                   (no candidate exchange at all)
+  both             owner absorbs candidates (depth, visited), then ONE all_gather carries the new frontier
+                   slice together with the two Beamer counters (|F|, Σdeg F), so direction choice and
+                   termination are decided identically on every rank with no extra all_reduce.
+
+Local work runs in the CUDA library through ``ess_bfs_partition_step`` / ``ess_bfs_absorb``
+(include/essentials_b200.h).  The class takes the local step as a *backend* object so the exchange logic can
+be exercised on CPU with the gloo backend (tests/test_dist_gloo.py supplies a numpy backend); the product
+backend is :class:`CudaBackend` and there is no CPU fallback in it.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_int64
+
+import torch
+import torch.distributed as dist
+
+INF = 2**31 - 1
+
+
+class CudaBackend:
+    """Local level kernels of one rank, in libessentials_b200.so."""
+
+    def __init__(self, csr_local, row_begin: int, n_global: int, device, stream):
+        import essentials_b200 as ess
+        self.ess = ess
+        self.ctx = ess.Context(device.index, stream=stream)
+        self.graph = ess.Graph(csr_local, symmetric=True)
+        self.row_begin, self.n_global = row_begin, n_global
+
+    def step(self, pull: bool, frontier_bits, visited_bits, candidate_bits):
+        ess = self.ess
+        ess._check(ess.lib().ess_bfs_partition_step(self.ctx.handle, self.graph.handle, self.row_begin, self.n_global,
+                                                    int(pull), ess._p(frontier_bits), ess._p(visited_bits),
+                                                    ess._p(candidate_bits)), "ess_bfs_partition_step")
+
+    def absorb(self, level: int, candidate_bits, visited_bits, next_bits, depth_local):
+        ess = self.ess
+        fv, fe = c_int64(0), c_int64(0)
+        ess._check(ess.lib().ess_bfs_absorb(self.ctx.handle, self.graph.handle, self.row_begin, self.n_global, level,
+                                            ess._p(candidate_bits), ess._p(visited_bits), ess._p(next_bits),
+                                            ess._p(depth_local), byref(fv), byref(fe)), "ess_bfs_absorb")
+        return fv.value, fe.value
+
+    def launches(self) -> int:
+        return self.ctx.launches()
+
+
+def _or_reduce_rows(t: torch.Tensor) -> torch.Tensor:
+    """Bitwise OR over dim 0 of an int32 matrix."""
+    out = t[0].clone()
+    for i in range(1, t.shape[0]):
+        out.bitwise_or_(t[i])
+    return out
+
+
+class PartitionedBFS:
+    """Direction-optimising BFS over a 1-D partitioned symmetric graph."""
+
+    def __init__(self, csr_local, row_begin: int, n_global: int, rank: int, world: int, backend, device,
+                 alpha: float = 14.0, beta: float = 24.0):
+        assert n_global % (32 * world) == 0, "partition boundaries must be multiples of 32 vertices"
+        self.rank, self.world, self.device, self.backend = rank, world, device, backend
+        self.n_global, self.per = n_global, n_global // world
+        self.row_begin = row_begin
+        assert row_begin == rank * self.per and csr_local.offsets.numel() - 1 == self.per
+        self.csr = csr_local
+        self.alpha, self.beta = alpha, beta
+        self.words = n_global // 32
+        self.wper = self.per // 32
+        i32 = dict(dtype=torch.int32, device=device)
+        self.frontier_bits = torch.zeros(self.words, **i32)
+        self.visited_bits = torch.zeros(self.words + 1, **i32)
+        self.candidate_bits = torch.zeros(self.words + 1, **i32)
+        self.next_bits = torch.zeros(self.words + 1, **i32)
+        self.depth_local = torch.empty(self.per, **i32)
+        # payload of the per-level all_gather: the owned frontier slice + (|fresh|, Σdeg fresh) as 2 x int64
+        self.send = torch.zeros(self.wper + 4, **i32)
+        self.recv = torch.zeros(world * (self.wper + 4), **i32)
+        self.a2a_recv = torch.zeros(self.words, **i32)
+        self.deg_local = (csr_local.offsets[1:] - csr_local.offsets[:-1]).to(torch.int64)
+        m = torch.tensor([int(csr_local.indices.numel())], dtype=torch.int64, device=device)
+        dist.all_reduce(m)
+        self.m_global = int(m.item())
+        self.offset_bits = 64 if csr_local.offsets.element_size() == 8 else 32
+        # isolated vertices never join a frontier: mark them visited once (replicated map)
+        iso_local = _pack_bits(self.deg_local == 0)
+        iso = torch.empty(self.words, **i32)
+        dist.all_gather_into_tensor(iso, iso_local)
+        self.isolated_bits = iso
+        self.levels = self.pull_levels = 0
+        self.bytes_exchanged = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def owner(self, v: int) -> int:
+        return v // self.per
+
+    def bfs(self, source: int) -> dict:
+        """Runs one BFS; depths of the owned range end up in self.depth_local. Returns per-run statistics."""
+        dev = self.device
+        self.visited_bits[: self.words].copy_(self.isolated_bits)
+        self.frontier_bits.zero_()
+        self.depth_local.fill_(INF)
+        word, bit = source // 32, source % 32
+        mask = _bit(bit)
+        self.frontier_bits[word] = mask
+        self.visited_bits[word] |= mask
+        local = torch.zeros(2, dtype=torch.int64, device=dev)
+        if self.owner(source) == self.rank:
+            self.depth_local[source - self.row_begin] = 0
+            local[0] = 1
+            local[1] = self.deg_local[source - self.row_begin]
+        dist.all_reduce(local)
+        n_f, m_f = (int(x) for x in local.tolist())
+        m_u = self.m_global - m_f
+        prev_n_f, pulling, level, pulls, exchanged = 0, False, 0, 0, 0
+        lo_w, hi_w = self.rank * self.wper, (self.rank + 1) * self.wper
+        while n_f > 0:
+            level += 1
+            if not pulling:
+                if m_f > m_u / self.alpha and n_f > prev_n_f:
+                    pulling = True
+            elif n_f < self.n_global / self.beta and n_f < prev_n_f:
+                pulling = False
+            self.backend.step(pulling, self.frontier_bits, self.visited_bits, self.candidate_bits)
+            if pulling:
+                pulls += 1
+            else:
+                # candidate slices go to their owners; the owner ORs the P contributions
+                dist.all_to_all_single(self.a2a_recv, self.candidate_bits[: self.words])
+                self.candidate_bits[lo_w:hi_w] = _or_reduce_rows(self.a2a_recv.view(self.world, self.wper))
+                exchanged += (self.world - 1) * self.wper * 4
+            fv, fe = self.backend.absorb(level, self.candidate_bits, self.visited_bits, self.next_bits,
+                                         self.depth_local)
+            self.send[: self.wper].copy_(self.next_bits[lo_w:hi_w])
+            self.send[self.wper:].copy_(torch.tensor([fv, fe], dtype=torch.int64).view(torch.int32))
+            dist.all_gather_into_tensor(self.recv, self.send)
+            exchanged += (self.world - 1) * (self.wper + 4) * 4
+            rows = self.recv.view(self.world, self.wper + 4)
+            self.frontier_bits.view(self.world, self.wper).copy_(rows[:, : self.wper])
+            self.visited_bits[: self.words].bitwise_or_(self.frontier_bits)
+            counts = rows[:, self.wper:].contiguous().view(torch.int64).sum(0).tolist()  # the one host sync
+            prev_n_f, n_f, m_f = n_f, int(counts[0]), int(counts[1])
+            m_u -= m_f
+        self.levels, self.pull_levels, self.bytes_exchanged = level, pulls, exchanged
+        return {"iterations": level, "pull_steps": pulls, "push_steps": level - pulls,
+                "nvlink_bytes_received": exchanged, "enact_ms": 0.0}
+
+    def reached_work(self):
+        """(n', m') of the last BFS, summed over ranks."""
+        r = self.depth_local != INF
+        t = torch.stack([r.sum().to(torch.int64), self.deg_local[r].sum()])
+        dist.all_reduce(t)
+        return int(t[0]), int(t[1])
+
+    def gather_depth(self) -> torch.Tensor:
+        """Full depth array on every rank (tests and validation)."""
+        full = torch.empty(self.n_global, dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(full, self.depth_local)
+        return full
+
+    def pick_sources(self, count: int, seed: int = 2) -> list[int]:
+        """Same seeded candidate stream as graphgen.pick_sources; owners vote on which are non-isolated."""
+        from .graphgen import mix64
+        pool = 64 * count + 1024
+        idx = torch.arange(pool, dtype=torch.int64) + seed * 1000003
+        cand = (mix64(idx) % self.n_global).to(self.device)
+        mine = (cand >= self.row_begin) & (cand < self.row_begin + self.per)
+        ok = torch.zeros(pool, dtype=torch.int32, device=self.device)
+        ok[mine] = (self.deg_local[cand[mine] - self.row_begin] > 0).to(torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MAX)
+        out = []
+        for v, good in zip(cand.tolist(), ok.tolist()):
+            if good and v not in out:
+                out.append(v)
+            if len(out) == count:
+                break
+        return out
+
+
+def _bit(b: int) -> int:
+    """int32 value with only bit b set (bit 31 is the sign bit)."""
+    return -(1 << 31) if b == 31 else (1 << b)
+
+
+def _pack_bits(flags: torch.Tensor) -> torch.Tensor:
+    """bool[n] (n % 32 == 0) -> int32[n/32], bit i of word w = flags[32w+i]."""
+    f = flags.view(-1, 32).to(torch.int64)
+    weights = (torch.ones(32, dtype=torch.int64, device=flags.device) << torch.arange(32, device=flags.device))
+    word = (f * weights).sum(1)
+    word = torch.where(word >= (1 << 31), word - (1 << 32), word)
+    return word.to(torch.int32)
+
+
+def build_partitioned(scale: int, edge_factor: int, rank: int, world: int, device, stream=None, seed: int = 1):
+    """Product constructor: regenerate the counter-based Kronecker edge list, keep this rank's rows, bind the
+    CUDA backend."""
+    from . import graphgen as gg
+    n = 1 << scale
+    per = n // world
+    ctxmgr = torch.cuda.stream(stream) if stream is not None else _null()
+    with ctxmgr:
+        csr = gg.rmat_csr(scale, edge_factor, seed=seed, device=device, row_range=(rank * per, (rank + 1) * per))
+        backend = CudaBackend(csr, rank * per, n, device, stream if stream is not None else torch.cuda.current_stream())
+        return PartitionedBFS(csr, rank * per, n, rank, world, backend, device)
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
