@@ -51,6 +51,7 @@ _SIGNATURES = {
     "ess_context_create": (c_int, [c_int, c_void_p, c_int, POINTER(c_void_p)]),
     "ess_context_destroy": (c_int, [c_void_p]),
     "ess_context_synchronize": (c_int, [c_void_p]),
+    "ess_tune": (c_int, [c_char_p, c_int]),
     "ess_profile_enable": (c_int, [c_void_p, c_int]),
     "ess_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "ess_graph_create": (c_int, [c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
@@ -98,6 +99,11 @@ def _check(code: int, what: str):
     if code != 0:
         msg = lib().ess_last_error()
         raise EssentialsError(f"{what} failed ({code}): {msg.decode() if msg else ''}")
+
+
+def tune(knob: str, value: int):
+    """Development knobs of the library (ess_tune)."""
+    _check(lib().ess_tune(knob.encode(), int(value)), "ess_tune")
 
 
 def _p(t):

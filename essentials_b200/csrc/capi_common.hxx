@@ -41,6 +41,10 @@ struct ess_graph_s {
   int64_t n = 0, m = 0;
   ess::graph_of<int32_t> g32;
   ess::graph_of<int64_t> g64;
+  // bottom-up hints owned by the handle (graph::build::pull_hints)
+  gunrock::memory::device_array_t<int32_t> hint_head;
+  gunrock::memory::device_array_t<int32_t> hint_edge32;
+  gunrock::memory::device_array_t<int64_t> hint_edge64;
 };
 
 #define ESS_TRY try {

@@ -56,6 +56,21 @@ int ess_context_synchronize(ess_context_t ctx) {
   ESS_CATCH
 }
 
+int ess_tune(const char* knob, int value) {
+  ESS_TRY
+  const std::string k = knob ? knob : "";
+  if (k == "pull_hints") {
+    gunrock::operators::advance::kernels::pull_hints_enabled() = value;
+    return 0;
+  }
+  if (k == "pull_variant") {
+    gunrock::operators::advance::kernels::pull_variant() = value;
+    return 0;
+  }
+  return ess::fail("ess_tune: unknown knob");
+  ESS_CATCH
+}
+
 int ess_profile_enable(ess_context_t ctx, int enable) {
   ESS_TRY
   auto& prof = ctx->single()->profiler();
@@ -112,6 +127,16 @@ int ess_graph_create(int64_t n, int64_t m, int offset_bits, const void* d_row_of
   else
     h->g32 = graph::build::from_csr_and_csc<int32_t, int32_t, float>(
         int32_t(n), int32_t(m), (int32_t*)d_row_offsets, J, X, (int32_t*)t_off, I, Xt);
+  if (h->has_csc && n > 0 && m > 0) {  // acceleration structure of the bottom-up advance, once per graph
+    h->hint_head.resize(std::size_t(n));
+    if (offset_bits == 64) {
+      h->hint_edge64.resize(std::size_t(n));
+      graph::build::pull_hints(h->g64, h->hint_head.data(), h->hint_edge64.data());
+    } else {
+      h->hint_edge32.resize(std::size_t(n));
+      graph::build::pull_hints(h->g32, h->hint_head.data(), h->hint_edge32.data());
+    }
+  }
   *out = h;
   return 0;
   ESS_CATCH

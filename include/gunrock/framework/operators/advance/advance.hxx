@@ -159,6 +159,15 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
       }
       prof.end(stream);
     } else if constexpr (lb == load_balance_t::merge_path || lb == load_balance_t::merge_path_v2) {
+      if (nf <= std::size_t(kernels::tile_edges)) {  // tiny level: one launch, table built per CTA
+        const long long maxdeg = max_degree(ctx, A.offsets, A.n);
+        long double bound = (long double)nf * (long double)maxdeg / kernels::tile_edges + 1;
+        const std::size_t tiles = bound > 1e9L ? std::size_t(1000000000) : std::size_t(bound);
+        prof.begin(profiler_t::push_expand, stream);
+        kernels::merge_path_small_kernel<graph_input, has_output, policy>
+            <<<gcuda::persistent_grid(ctx, tiles, 6), 256, 0, stream>>>(A, op, in, int(nf), out, C, capacity, visited);
+        prof.end(stream);
+      } else {
       if (segments.size() < nf + 1) segments.resize(nf + 1);
       gcuda::arena_layout_t layout;
       const std::size_t at_src = layout.add((nf + 1) * sizeof(vertex_t));
@@ -179,6 +188,7 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
           <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(A, op, work_src, work_beg, work_seg,
                                                                                 out, C, capacity, visited);
       prof.end(stream);
+      }
     } else if constexpr (lb == load_balance_t::bucketing) {
       gcuda::arena_layout_t layout;
       const std::size_t at_small = layout.add(nf * sizeof(vertex_t));
@@ -236,7 +246,8 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
   using gcuda::profiler_t;
   auto stream = ctx.stream();
   const auto out_adj = graph::adjacency_of<false>(G);
-  const auto in_adj = graph::adjacency_of<true>(G);
+  auto in_adj = graph::adjacency_of<true>(G);
+  if (!kernels::pull_hints_enabled()) in_adj.head = nullptr;
   const vertex_t n = out_adj.n;
   auto* input = E->get_input_frontier();
   auto* output = E->get_output_frontier();
@@ -285,8 +296,20 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
     auto& nxt = D.dense[D.dense_selector ^ 1];
     scratch.zero(stream);
     prof.begin(profiler_t::pull_step, stream);
-    kernels::pull_step_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 8), 256, 0, stream>>>(
-        in_adj, op, cur.data(), nxt.data(), D.visited.data(), scratch.d);
+    const unsigned pull_grid = gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 8);
+    switch (kernels::pull_variant()) {
+      case 0:
+        kernels::pull_step_kernel<false><<<pull_grid, 256, 0, stream>>>(in_adj, op, cur.data(), nxt.data(),
+                                                                         D.visited.data(), scratch.d);
+        break;
+      case 2:
+        kernels::pull_step_staged_kernel<<<pull_grid, 256, 0, stream>>>(in_adj, op, cur.data(), nxt.data(),
+                                                                        D.visited.data(), scratch.d);
+        break;
+      default:
+        kernels::pull_step_kernel<true><<<pull_grid, 256, 0, stream>>>(in_adj, op, cur.data(), nxt.data(),
+                                                                        D.visited.data(), scratch.d);
+    }
     prof.end(stream);
     error::check_last("pull step");
     scratch.fetch(stream);
@@ -308,16 +331,10 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
     D.push_vertices_expanded += D.frontier_vertices;
     D.push_edges_expanded += D.frontier_edges;
     grow_output(output, std::size_t(n));
-    // Σdeg of the new frontier (Beamer's m_f) is accumulated by a follow-up kernel that reads the output
-    // length from the device counter, so the whole level still costs a single host synchronisation.
-    auto degree_sum_of_output = [&](counter_t* C, vertex_t* out) {
-      prof.begin(profiler_t::dense_state, stream);
-      kernels::mark_frontier_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 2), 256, 0, stream>>>(
-          out_adj.offsets, out, std::size_t(0), C + scratch_t::out_count, (unsigned*)nullptr, C);
-      prof.end(stream);
-    };
+    // Σdeg of the new frontier (Beamer's m_f) is accumulated inside the expansion kernels (test-and-set
+    // policy adds the out-degree of every vertex it marks), so the level costs a single synchronisation.
     expand<lb, false, input_type, output_type, visit_t::test_and_set>(G, op, input, output, E->scanned_work_domain, ctx,
-                                                                     D.visited.data(), degree_sum_of_output);
+                                                                     D.visited.data());
     next_vertices = (long long)output->get_number_of_elements();
     next_edges = next_vertices ? (long long)scratch.h[scratch_t::aux2] : 0;
     ++D.push_steps;

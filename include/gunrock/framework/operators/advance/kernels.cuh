@@ -51,10 +51,12 @@ constexpr int warp_degree = 32;                       // bucketing: lists at lea
 /// Visited-bitmap handling of an advance: `none` = reference semantics (operator runs on every edge).
 enum class visit_t { none, test_and_set };
 
+/// `fresh_edges` (test_and_set only) accumulates the out-degree of every vertex this thread adds to the
+/// visited set: Σdeg of the next frontier is Beamer's m_f, needed by the push/pull switch.
 template <visit_t policy, typename vertex_t, typename edge_t, typename weight_t, typename operator_t>
 __device__ __forceinline__ bool visit_edge(const graph::adjacency_t<vertex_t, edge_t, weight_t>& A,
                                            operator_t& op, vertex_t source, edge_t edge, vertex_t neighbor,
-                                           unsigned* __restrict__ visited) {
+                                           unsigned* __restrict__ visited, counter_t& fresh_edges) {
   if constexpr (policy == visit_t::test_and_set) {
     if ((visited[unsigned(neighbor) >> 5] >> (unsigned(neighbor) & 31u)) & 1u) return false;
   }
@@ -64,9 +66,20 @@ __device__ __forceinline__ bool visit_edge(const graph::adjacency_t<vertex_t, ed
     if (keep) {
       const unsigned bit = 1u << (unsigned(neighbor) & 31u);
       keep = !(atomicOr(&visited[unsigned(neighbor) >> 5], bit) & bit);
+      if (keep) fresh_edges += counter_t(A.offsets[neighbor + 1] - A.offsets[neighbor]);
     }
   }
   return keep;
+}
+
+/// End-of-kernel flush of a thread's fresh_edges into counters[aux2] (one atomic per warp).
+template <visit_t policy>
+__device__ __forceinline__ void flush_fresh_edges(counter_t fresh_edges, counter_t* counters) {
+  if constexpr (policy == visit_t::test_and_set) {
+    __syncwarp();
+    fresh_edges = b200::warp_sum(fresh_edges);
+    if (b200::lane_id() == 0 && fresh_edges) atomicAdd(counters + scratch_t::aux2, fresh_edges);
+  }
 }
 
 /// Shared-memory description of the work a CTA expands in one go.
@@ -90,7 +103,10 @@ template <bool has_output, visit_t policy, typename vertex_t, typename edge_t, t
 __device__ __forceinline__ void expand_tile(const graph::adjacency_t<vertex_t, edge_t, weight_t>& A, operator_t& op,
                                             tile_smem_t<vertex_t, edge_t>& sm, int n_seg, edge_t n_edges,
                                             vertex_t* __restrict__ output, counter_t* counters, counter_t capacity,
-                                            unsigned* __restrict__ visited) {
+                                            unsigned* __restrict__ visited, counter_t& fresh_edges,
+                                            edge_t edge_base = 0) {
+  // edge_base: when the segment table covers more than this tile (small-frontier kernel), tile edge r is
+  // edge (edge_base + r) of the table.
   for (edge_t round = 0; round < n_edges; round += tile_edges) {
     vertex_t nbr[tile_items];
     vertex_t src[tile_items];
@@ -100,9 +116,10 @@ __device__ __forceinline__ void expand_tile(const graph::adjacency_t<vertex_t, e
     for (int i = 0; i < tile_items; ++i) {
       edge_t r = round + edge_t(i * cta_threads + threadIdx.x);
       if (r < n_edges) {
-        int j = n_seg == 1 ? 0 : b200::upper_segment(sm.seg, n_seg, r);
+        const edge_t at = r + edge_base;
+        int j = n_seg == 1 ? 0 : b200::upper_segment(sm.seg, n_seg, at);
         src[i] = sm.src[j];
-        eid[i] = sm.beg[j] + (r - sm.seg[j]);
+        eid[i] = sm.beg[j] + (at - sm.seg[j]);
         live |= 1u << i;
       }
     }
@@ -113,7 +130,7 @@ __device__ __forceinline__ void expand_tile(const graph::adjacency_t<vertex_t, e
 #pragma unroll
     for (int i = 0; i < tile_items; ++i)
       if (live & (1u << i))
-        if (visit_edge<policy>(A, op, src[i], eid[i], nbr[i], visited)) keep |= 1u << i;
+        if (visit_edge<policy>(A, op, src[i], eid[i], nbr[i], visited, fresh_edges)) keep |= 1u << i;
     if constexpr (has_output)
       b200::cta_append<cta_threads, tile_items>(nbr, keep, output, counters + scratch_t::out_count, capacity,
                                                 sm.append);
@@ -173,6 +190,7 @@ __global__ void __launch_bounds__(cta_threads)
   if constexpr (has_output && guard)
     if (!output_fits(counters, capacity)) return;
   if (size_ptr) input_size = std::size_t(*size_ptr);
+  counter_t fresh_edges = 0;
   for (std::size_t base = std::size_t(blockIdx.x) * cta_threads; base < input_size;
        base += std::size_t(gridDim.x) * cta_threads) {
     const std::size_t i = base + threadIdx.x;
@@ -191,7 +209,7 @@ __global__ void __launch_bounds__(cta_threads)
       vertex_t nbr = 0;
       if (k < deg) {
         nbr = __ldg(A.indices + beg + k);
-        keep = visit_edge<policy>(A, op, v, edge_t(beg + k), nbr, visited);
+        keep = visit_edge<policy>(A, op, v, edge_t(beg + k), nbr, visited, fresh_edges);
       }
       if constexpr (has_output) {
         const unsigned votes = __ballot_sync(b200::full_mask, keep);
@@ -202,6 +220,7 @@ __global__ void __launch_bounds__(cta_threads)
       }
     }
   }
+  flush_fresh_edges<policy>(fresh_edges, counters);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -217,6 +236,7 @@ __global__ void __launch_bounds__(cta_threads)
   const std::size_t count = std::size_t(*size_ptr);
   const unsigned lane = b200::lane_id();
   const std::size_t warps = (std::size_t(gridDim.x) * cta_threads) >> 5;
+  counter_t fresh_edges = 0;
   for (std::size_t item = (std::size_t(blockIdx.x) * cta_threads + threadIdx.x) >> 5; item < count; item += warps) {
     vertex_t v = list[item];
     const edge_t beg = A.offsets[v], end = A.offsets[v + 1];
@@ -226,7 +246,7 @@ __global__ void __launch_bounds__(cta_threads)
       vertex_t nbr = 0;
       if (e < end) {
         nbr = __ldg(A.indices + e);
-        keep = visit_edge<policy>(A, op, v, e, nbr, visited);
+        keep = visit_edge<policy>(A, op, v, e, nbr, visited, fresh_edges);
       }
       if constexpr (has_output) {
         const unsigned votes = __ballot_sync(b200::full_mask, keep);
@@ -237,6 +257,7 @@ __global__ void __launch_bounds__(cta_threads)
       }
     }
   }
+  flush_fresh_edges<policy>(fresh_edges, counters);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -251,6 +272,7 @@ __global__ void __launch_bounds__(cta_threads)
   __shared__ tile_smem_t<vertex_t, edge_t> sm;
   if constexpr (has_output && guard)
     if (!output_fits(counters, capacity)) return;
+  counter_t fresh_edges = 0;
   for (std::size_t base = std::size_t(blockIdx.x) * cta_threads; base < input_size;
        base += std::size_t(gridDim.x) * cta_threads) {
     const std::size_t i = base + threadIdx.x;
@@ -279,9 +301,11 @@ __global__ void __launch_bounds__(cta_threads)
     }
     __syncthreads();
     if (n_edges > 0)
-      expand_tile<has_output, policy>(A, op, sm, int(n_seg), n_edges, output, counters, capacity, visited);
+      expand_tile<has_output, policy>(A, op, sm, int(n_seg), n_edges, output, counters, capacity, visited,
+                                      fresh_edges);
     __syncthreads();
   }
+  flush_fresh_edges<policy>(fresh_edges, counters);
 }
 
 /// Grid-wide expansion of the deferred hubs: every CTA strides the 1024-edge tiles of each listed vertex.
@@ -294,6 +318,7 @@ __global__ void __launch_bounds__(cta_threads)
   if constexpr (has_output)
     if (!output_fits(counters, capacity)) return;
   const std::size_t count = std::size_t(*size_ptr);
+  counter_t fresh_edges = 0;
   for (std::size_t item = 0; item < count; ++item) {
     const vertex_t v = big_list[item];
     const edge_t beg = A.offsets[v], deg = A.offsets[v + 1] - beg;
@@ -306,10 +331,11 @@ __global__ void __launch_bounds__(cta_threads)
       __syncthreads();
       const edge_t left = deg - t0;
       expand_tile<has_output, policy>(A, op, sm, 1, left < edge_t(tile_edges) ? left : edge_t(tile_edges), output,
-                                      counters, capacity, visited);
+                                      counters, capacity, visited, fresh_edges);
       __syncthreads();
     }
   }
+  flush_fresh_edges<policy>(fresh_edges, counters);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -409,6 +435,7 @@ __global__ void __launch_bounds__(cta_threads)
     if (!output_fits(counters, capacity)) return;
   const long long total = (long long)counters[scratch_t::work_total];
   const long long n_items = (long long)counters[scratch_t::items];
+  counter_t fresh_edges = 0;
   for (long long g0 = (long long)blockIdx.x * tile_edges; g0 < total; g0 += (long long)gridDim.x * tile_edges) {
     const long long g1 = g0 + tile_edges < total ? g0 + tile_edges : total;
     if (threadIdx.x == 0 || threadIdx.x == 32) {  // two lanes of two warps search the slice ends in parallel
@@ -433,9 +460,72 @@ __global__ void __launch_bounds__(cta_threads)
       sm.seg[j] = edge_t(s < g0 ? 0 : s - g0);
     }
     __syncthreads();
-    expand_tile<has_output, policy>(A, op, sm, n_seg, edge_t(g1 - g0), output, counters, capacity, visited);
+    expand_tile<has_output, policy>(A, op, sm, n_seg, edge_t(g1 - g0), output, counters, capacity, visited,
+                                    fresh_edges);
     __syncthreads();
   }
+  flush_fresh_edges<policy>(fresh_edges, counters);
+}
+
+// merge_path for small frontiers (nf <= tile_edges items): ONE launch. Every CTA redundantly builds the whole
+// (source, first edge, scanned offset) table in shared memory — at most 1024 row-bound pairs, L2 hits — and
+// then expands its own equal slices of the edge range straight from that table. Replaces the
+// memset + prepare_work_kernel + merge_path_kernel sequence on the many tiny levels of a BFS
+// (source level, the first hops, the tail) where launch latency, not bandwidth, is the cost.
+template <bool graph_input, bool has_output, visit_t policy, typename vertex_t, typename edge_t, typename weight_t,
+          typename operator_t>
+__global__ void __launch_bounds__(cta_threads)
+    merge_path_small_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op,
+                            const vertex_t* __restrict__ input, int input_size, vertex_t* __restrict__ output,
+                            counter_t* counters, counter_t capacity, unsigned* __restrict__ visited) {
+  __shared__ tile_smem_t<vertex_t, edge_t> sm;
+  vertex_t v[tile_items];
+  edge_t beg[tile_items], deg[tile_items];
+  unsigned my_items = 0;
+  edge_t my_edges = 0;
+#pragma unroll
+  for (int k = 0; k < tile_items; ++k) {
+    const int i = int(threadIdx.x) * tile_items + k;  // blocked order keeps the table in frontier order
+    v[k] = gunrock::numeric_limits<vertex_t>::invalid();
+    beg[k] = deg[k] = 0;
+    if (i < input_size) {
+      v[k] = graph_input ? vertex_t(i) : input[i];
+      if (util::limits::is_valid(v[k])) {
+        beg[k] = A.offsets[v[k]];
+        deg[k] = A.offsets[v[k] + 1] - beg[k];
+      }
+    }
+    my_items += deg[k] > 0;
+    my_edges += deg[k];
+  }
+  unsigned n_seg;
+  edge_t total;
+  unsigned at = b200::cta_exclusive_sum<cta_threads, unsigned>(my_items, n_seg, sm.scan_u);
+  edge_t run = b200::cta_exclusive_sum<cta_threads, edge_t>(my_edges, total, sm.scan_e);
+#pragma unroll
+  for (int k = 0; k < tile_items; ++k)
+    if (deg[k] > 0) {
+      sm.src[at] = v[k];
+      sm.beg[at] = beg[k];
+      sm.seg[at] = run;
+      ++at;
+      run += deg[k];
+    }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) counters[scratch_t::work_total] = counter_t(total);
+  if constexpr (has_output) {
+    if (counter_t(total) > capacity) {  // every CTA computes the same total, so all of them leave
+      if (blockIdx.x == 0 && threadIdx.x == 0) counters[scratch_t::overflow] = counter_t(total);
+      return;
+    }
+  }
+  counter_t fresh_edges = 0;
+  for (edge_t g0 = edge_t(blockIdx.x) * tile_edges; g0 < total; g0 += edge_t(gridDim.x) * tile_edges) {
+    const edge_t left = total - g0;
+    expand_tile<has_output, policy>(A, op, sm, int(n_seg), left < edge_t(tile_edges) ? left : edge_t(tile_edges),
+                                    output, counters, capacity, visited, fresh_edges, g0);
+  }
+  flush_fresh_edges<policy>(fresh_edges, counters);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -103,6 +103,43 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+/// head[v] = in-neighbour of v with the largest degree (ties: first in the list), head_edge[v] = that in-edge;
+/// head[v] = -1 for vertices without in-edges. `degree_offsets` is the offsets array degrees are read from
+/// (the CSR when present, so "degree" is the out-degree of the in-neighbour). One warp per vertex.
+template <typename vertex_t, typename edge_t>
+__global__ void __launch_bounds__(256)
+    pull_hints_kernel(vertex_t n, const edge_t* __restrict__ in_offsets, const vertex_t* __restrict__ in_indices,
+                      const edge_t* __restrict__ degree_offsets, vertex_t* __restrict__ head,
+                      edge_t* __restrict__ head_edge) {
+  const unsigned lane = threadIdx.x & 31;
+  const std::size_t warps = (std::size_t(gridDim.x) * blockDim.x) >> 5;
+  for (std::size_t v = (std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; v < std::size_t(n); v += warps) {
+    const edge_t b = in_offsets[v], e = in_offsets[v + 1];
+    long long best_deg = -1;
+    edge_t best_edge = e;
+    for (edge_t k = b + lane; k < e; k += 32) {
+      const vertex_t u = in_indices[k];
+      const long long d = (long long)(degree_offsets[u + 1] - degree_offsets[u]);
+      if (d > best_deg) {  // strict: keeps the earliest edge of this lane on ties
+        best_deg = d;
+        best_edge = k;
+      }
+    }
+    for (int s = 16; s > 0; s >>= 1) {  // (degree desc, edge asc) arg-max across the warp
+      const long long od = __shfl_xor_sync(0xffffffffu, best_deg, s);
+      const edge_t oe = __shfl_xor_sync(0xffffffffu, best_edge, s);
+      if (od > best_deg || (od == best_deg && oe < best_edge)) {
+        best_deg = od;
+        best_edge = oe;
+      }
+    }
+    if (lane == 0) {
+      head[v] = best_deg >= 0 ? in_indices[best_edge] : vertex_t(-1);
+      head_edge[v] = best_deg >= 0 ? best_edge : edge_t(-1);
+    }
+  }
+}
+
 template <typename vertex_t, typename edge_t, typename weight_t>
 void transpose_on_device(vertex_t n, edge_t m, const edge_t* Ap, const vertex_t* J, const weight_t* X,
                          vertex_t* I, edge_t* Aj, weight_t* csc_values) {
@@ -161,6 +198,32 @@ auto from_csr(vertex_t const& r, vertex_t const& c, edge_t const& nnz, edge_t* A
   }
   (void)c;
   return G;
+}
+
+/**
+ * @brief Fill caller-owned hint arrays (head[n], head_edge[n]) for the CSC view of G and attach them.
+ * Bottom-up advance probes head[v] first: it is read coalesced next to the row bounds, and the highest-degree
+ * in-neighbour is the likeliest to be in a BFS frontier, so most vertices never touch their adjacency list
+ * (one random 32-byte sector each otherwise). Setup cost, once per graph; results do not depend on it.
+ */
+template <typename graph_type>
+void pull_hints(graph_type& G, typename graph_type::vertex_type* head, typename graph_type::edge_type* head_edge,
+                cudaStream_t stream = 0) {
+  using csr_v = typename graph_type::graph_csr_view_t;
+  using csc_v = typename graph_type::graph_csc_view_t;
+  static_assert(graph_type::template contains_representation<csc_v>(), "pull hints belong to the CSC view");
+  csc_v& c = G;
+  const auto* degree_offsets = c.get_column_offsets();
+  if constexpr (graph_type::template contains_representation<csr_v>()) {
+    const csr_v& r = G;
+    if (r.get_row_offsets()) degree_offsets = r.get_row_offsets();
+  }
+  const auto n = c.get_number_of_vertices();
+  if (n > 0)
+    detail::pull_hints_kernel<<<2048, 256, 0, stream>>>(n, c.get_column_offsets(), c.get_row_indices(), degree_offsets,
+                                                        head, head_edge);
+  error::throw_if_exception(cudaStreamSynchronize(stream), "pull_hints");
+  c.set_pull_hints(head, head_edge);
 }
 
 /// Wrap pre-built CSR and CSC arrays (no computation): used by the C ABI when the caller owns both.

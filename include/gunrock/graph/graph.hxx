@@ -202,6 +202,13 @@ class graph_csc_t {
 
   __host__ __device__ __forceinline__ auto get_column_offsets() const { return s.offsets; }
   __host__ __device__ __forceinline__ auto get_row_indices() const { return s.indices; }
+  /// Bottom-up hints (B200 addition): caller-owned arrays filled by graph::build::pull_hints.
+  __host__ __device__ void set_pull_hints(const vertex_t* head, const edge_t* head_edge) {
+    hint_head = head;
+    hint_edge = head_edge;
+  }
+  __host__ __device__ __forceinline__ const vertex_t* get_pull_hint_heads() const { return hint_head; }
+  __host__ __device__ __forceinline__ const edge_t* get_pull_hint_edges() const { return hint_edge; }
   __host__ __device__ __forceinline__ auto get_nonzero_values() const { return s.values; }
   __host__ __device__ __forceinline__ auto get_number_of_rows() const { return s.number_of_vertices; }
   __host__ __device__ __forceinline__ auto get_number_of_columns() const { return s.number_of_vertices; }
@@ -221,6 +228,8 @@ class graph_csc_t {
 
  private:
   store_t s;
+  const vertex_t* hint_head = nullptr;
+  const edge_t* hint_edge = nullptr;
 };
 
 template <typename vertex_t, typename edge_t, typename weight_t>
@@ -397,6 +406,10 @@ struct adjacency_t {
   const weight_t* values;  // may be null: weight 1
   vertex_t n;
   edge_t m;
+  // Optional bottom-up hints (CSC only, see graph::build::pull_hints): for every vertex its in-neighbour of
+  // largest degree and the id of that in-edge; null when the graph was built without them.
+  const vertex_t* head = nullptr;
+  const edge_t* head_edge = nullptr;
 };
 
 /// The arrays an advance walks: CSR (rows -> out-neighbours) for forward, CSC (columns -> in-neighbours)
@@ -411,8 +424,9 @@ auto adjacency_of(const graph_type& G) {
     static_assert(graph_type::template contains_representation<csc_v>(),
                   "backward / direction-optimised advance needs a graph built with view_t::csc");
     const csc_v& c = G;
-    return adjacency_t<V, E, W>{c.get_column_offsets(), c.get_row_indices(), c.get_nonzero_values(),
-                                c.get_number_of_vertices(), c.get_number_of_edges()};
+    return adjacency_t<V, E, W>{c.get_column_offsets(), c.get_row_indices(),     c.get_nonzero_values(),
+                                c.get_number_of_vertices(), c.get_number_of_edges(), c.get_pull_hint_heads(),
+                                c.get_pull_hint_edges()};
   } else {
     using csr_v = typename graph_type::graph_csr_view_t;
     static_assert(graph_type::template contains_representation<csr_v>(),

@@ -14,6 +14,10 @@ ap.add_argument("--sources", type=int, default=4)
 ap.add_argument("--variants", default="block_mapped:forward,merge_path:forward,bucketing:forward,"
                                       "block_mapped:optimized,merge_path:optimized,bucketing:optimized")
 ap.add_argument("--sssp", action="store_true")
+ap.add_argument("--pull-variants", default="")
+ap.add_argument("--hints", default="1")
+ap.add_argument("--alphas", default="0")
+ap.add_argument("--betas", default="0")
 args = ap.parse_args()
 
 t = time.time()
@@ -25,11 +29,20 @@ g = ess.Graph(csr)
 srcs = gg.pick_sources(csr, args.sources)
 deg = csr.degrees().long()
 base = None
-for variant in args.variants.split(","):
+runs = [(v, None) for v in args.variants.split(",")]
+if args.pull_variants:
+    runs = [(v, int(pv)) for pv in args.pull_variants.split(",") for v in args.variants.split(",")]
+runs = [(v, pv, int(h), float(a), float(b)) for (v, pv) in runs for h in args.hints.split(",")
+        for a in args.alphas.split(",") for b in args.betas.split(",")]
+for variant, pv, hints, alpha, beta in runs:
     lb, direction = variant.split(":")
+    ess.tune("pull_hints", hints)
+    if pv is not None:
+        ess.tune("pull_variant", pv)
+    variant = f"{variant}/pv{pv}/h{hints}/a{alpha:g}/b{beta:g}"
     for s in srcs:
         ctx.profile(True)
-        depth, info = ess.bfs(ctx, g, s, lb=lb, direction=direction)
+        depth, info = ess.bfs(ctx, g, s, lb=lb, direction=direction, alpha=alpha, beta=beta)
         prof = ctx.profile_read()
         ctx.profile(False)
         reached = depth != 2**31 - 1
@@ -40,7 +53,7 @@ for variant in args.variants.split(","):
             assert torch.equal(base[s], depth), f"{variant} differs from the first variant at source {s}"
         else:
             base[s] = depth.clone()
-        print(f"{variant:28s} src={s:9d} enact={info['enact_ms']:9.3f} ms  levels={info['iterations']:3d} "
+        print(f"{variant:40s} src={s:9d} enact={info['enact_ms']:9.3f} ms  levels={info['iterations']:3d} "
               f"pull={info['pull_steps']}  reached={int(reached.sum())}  GTEPS={m_r/info['enact_ms']/1e6:8.2f}  "
               + " ".join(f"{k}={v[0]:.3f}ms/{v[1]}" for k, v in prof.items() if v[1])
               + f" pullV={info['pull_vertices']} pullE={info['pull_edges']} pushV={info['push_vertices']} pushE={info['push_edges']}",
