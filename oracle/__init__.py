@@ -22,6 +22,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_SO = os.path.join(_HERE, "liboracle.so")
 _REF_SO = os.path.join(_HERE, "_ref", "libref_cpu.so")
+_REF_GPU_SO = os.path.join(_HERE, "_ref", "libref_gpu.so")
 
 
 def build(verbose: bool = False) -> None:
@@ -237,3 +238,74 @@ def ref_randoms(n: int, lo: float, hi: float):
     out = np.empty(n, np.float32)
     ref().ref_randoms(n, lo, hi, _ptr(out))
     return out
+
+
+# ----------------------------------------------------------------------------- the reference's own GPU code
+_ref_gpu = None
+
+
+def have_ref_gpu() -> bool:
+    return os.path.exists(_REF_GPU_SO)
+
+
+def ref_gpu() -> ctypes.CDLL:
+    """The reference's GPU path (block_mapped advance + Thrust filters) built for sm_100 (oracle/_ref)."""
+    global _ref_gpu
+    if _ref_gpu is None:
+        if not have_ref_gpu():
+            raise RuntimeError("oracle/_ref/libref_gpu.so missing: run `make -C oracle refgpu` where /root/reference exists")
+        R = ctypes.CDLL(_REF_GPU_SO)
+        for name in ("ref_gpu_bfs", "ref_gpu_sssp", "ref_gpu_pr", "ref_gpu_ppr", "ref_gpu_kcore", "ref_gpu_color"):
+            getattr(R, name).restype = c_float
+        R.ref_gpu_bfs.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+        R.ref_gpu_sssp.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+        R.ref_gpu_pr.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]
+        R.ref_gpu_ppr.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]
+        R.ref_gpu_kcore.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+        R.ref_gpu_color.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+        _ref_gpu = R
+    return _ref_gpu
+
+
+def _gpu_args(csr):
+    """(n, m, offsets, indices, values) device pointers of an int32 CSR held in torch CUDA tensors."""
+    import torch
+    assert csr.offsets.dtype == torch.int32 and csr.offsets.is_cuda, "the reference drivers are int32-only"
+    vals = csr.values if csr.values is not None else torch.ones(csr.m, dtype=torch.float32, device=csr.indices.device)
+    csr._ref_vals = vals  # keep alive
+    return (int(csr.offsets.numel() - 1), int(csr.indices.numel()), c_void_p(csr.offsets.data_ptr()),
+            c_void_p(csr.indices.data_ptr()), c_void_p(vals.data_ptr()))
+
+
+def ref_gpu_run(alg: str, csr, *params):
+    """Runs gunrock::<alg>::run of the REFERENCE on the GPU. Returns (result tensor, enact ms)."""
+    import torch
+    n, m, off, col, val = _gpu_args(csr)
+    dev = csr.indices.device
+    torch.cuda.synchronize()
+    R = ref_gpu()
+    if alg == "bfs":
+        out = torch.empty(n, dtype=torch.int32, device=dev)
+        ms = R.ref_gpu_bfs(n, m, off, col, val, int(params[0]), c_void_p(out.data_ptr()))
+    elif alg == "sssp":
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        ms = R.ref_gpu_sssp(n, m, off, col, val, int(params[0]), c_void_p(out.data_ptr()))
+    elif alg == "pr":
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        ms = R.ref_gpu_pr(n, m, off, col, val, float(params[0]), float(params[1]), c_void_p(out.data_ptr()))
+    elif alg == "ppr":
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        ms = R.ref_gpu_ppr(n, m, off, col, val, int(params[0]), float(params[1]), float(params[2]),
+                           c_void_p(out.data_ptr()))
+    elif alg == "kcore":
+        out = torch.empty(n, dtype=torch.int32, device=dev)
+        ms = R.ref_gpu_kcore(n, m, off, col, val, c_void_p(out.data_ptr()))
+    elif alg == "color":
+        out = torch.empty(n, dtype=torch.int32, device=dev)
+        ms = R.ref_gpu_color(n, m, off, col, val, c_void_p(out.data_ptr()))
+    else:
+        raise ValueError(alg)
+    torch.cuda.synchronize()
+    if ms < 0:
+        raise RuntimeError(f"reference GPU {alg} failed")
+    return out, float(ms)

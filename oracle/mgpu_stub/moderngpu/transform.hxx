@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY: see context.hxx in this directory.
+#pragma once
+#include "context.hxx"
