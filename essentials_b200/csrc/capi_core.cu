@@ -63,10 +63,6 @@ int ess_tune(const char* knob, int value) {
     gunrock::operators::advance::kernels::pull_hints_enabled() = value;
     return 0;
   }
-  if (k == "pull_variant") {
-    gunrock::operators::advance::kernels::pull_variant() = value;
-    return 0;
-  }
   return ess::fail("ess_tune: unknown knob");
   ESS_CATCH
 }

@@ -73,7 +73,7 @@ ESS_API int ess_context_synchronize(ess_context_t ctx);
  * expansion, 2 work preparation (scan/binning), 3 dense-state kernels (sparse<->dense, visited), 4 filters.
  * ess_profile_enable resets the accumulators; ess_profile_read resolves pending events and copies
  * accumulated milliseconds and launch counts (arrays of n_classes <= 8 entries). */
-ESS_API int ess_tune(const char* knob, int value); /* development knobs, e.g. "pull_variant" (see pull.cuh) */
+ESS_API int ess_tune(const char* knob, int value); /* development knobs, e.g. "pull_hints" (see pull.cuh) */
 ESS_API int ess_profile_enable(ess_context_t ctx, int enable);
 ESS_API int ess_profile_read(ess_context_t ctx, double* ms_by_class, int64_t* launches_by_class, int n_classes);
 

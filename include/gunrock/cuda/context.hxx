@@ -74,9 +74,12 @@ struct scratch_t {
   void init() {
     if (d) return;
     error::throw_if_exception(cudaMalloc(&d, n_slots * sizeof(unsigned long long)), "scratch counters");
-    error::throw_if_exception(cudaMallocHost(&h, n_slots * sizeof(unsigned long long)), "scratch mirror");
+    // mapped pinned mirror: the publish kernel writes it directly, the host polls it (no DMA, no stream sync)
+    error::throw_if_exception(cudaHostAlloc(&h, (n_slots + 1) * sizeof(unsigned long long), cudaHostAllocMapped),
+                              "scratch mirror");
     error::throw_if_exception(cudaMemset(d, 0, n_slots * sizeof(unsigned long long)), "scratch memset");
-    for (int i = 0; i < n_slots; ++i) h[i] = 0;
+    for (int i = 0; i <= n_slots; ++i) h[i] = 0;
+    clean = true;
   }
   /// Temp arena of at least `bytes` (256-byte aligned sub-allocation is the caller's business).
   unsigned char* temp(std::size_t bytes) {
@@ -84,13 +87,50 @@ struct scratch_t {
       arena.reserve(bytes + bytes / 2 + 4096, /*keep=*/false);
     return arena.data();
   }
-  void zero(stream_t s) { cudaMemsetAsync(d, 0, n_slots * sizeof(unsigned long long), s); }
-  /// Copies the counter block to the pinned mirror and waits for the stream: one sync per operator.
-  void fetch(stream_t s) {
-    cudaMemcpyAsync(h, d, n_slots * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
-    error::throw_if_exception(cudaStreamSynchronize(s), "operator stream sync");
+  /// Counters are zero after every fetch(); this only has to act when a caller skipped its fetch().
+  void zero(stream_t s) {
+    if (!clean) cudaMemsetAsync(d, 0, n_slots * sizeof(unsigned long long), s);
+    clean = false;
   }
+  /// Publishes the counter block to the host mirror, re-zeroes it on the device and waits for it:
+  /// the ONE host<->device round trip of an operator call. See publish_counters_kernel below.
+  inline void fetch(stream_t s);
+
+  bool clean = false;
+  unsigned long long sequence = 0;  // value the host waits for in h[n_slots]
 };
+
+/// Copies the counters to mapped host memory, zeroes them for the next operator, then raises the sequence
+/// flag the host spins on. One warp. Replaces cudaMemcpyAsync(D2H) + cudaStreamSynchronize: the host sees the
+/// result a PCIe write after the last kernel finished instead of after a DMA + driver wake-up.
+static __global__ void publish_counters_kernel(unsigned long long* d, volatile unsigned long long* h,
+                                               unsigned long long sequence) {
+  const int i = threadIdx.x;
+  if (i < scratch_t::n_slots) {
+    h[i] = d[i];
+    d[i] = 0;
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (i == 0) h[scratch_t::n_slots] = sequence;
+}
+
+inline void scratch_t::fetch(stream_t s) {
+  ++sequence;
+  publish_counters_kernel<<<1, 32, 0, s>>>(d, h, sequence);
+  volatile unsigned long long* flag = h + n_slots;
+  for (unsigned spins = 0; *flag != sequence; ++spins) {
+    if ((spins & 0x3ff) == 0x3ff) {  // every ~1k polls make sure the stream is still healthy
+      cudaError_t st = cudaStreamQuery(s);
+      if (st != cudaSuccess && st != cudaErrorNotReady) error::throw_if_exception(st, "operator stream");
+      if (st == cudaSuccess && *flag != sequence) {  // stream drained: the flag write must be visible now
+        error::throw_if_exception(cudaStreamSynchronize(s), "operator stream sync");
+        if (*flag != sequence) error::throw_if_exception(cudaErrorUnknown, "counter publish lost");
+      }
+    }
+  }
+  clean = true;
+}
 
 /**
  * @brief Opt-in per-kernel-class timing with CUDA events on the launching stream (bench/roofline use).

@@ -296,20 +296,8 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
     auto& nxt = D.dense[D.dense_selector ^ 1];
     scratch.zero(stream);
     prof.begin(profiler_t::pull_step, stream);
-    const unsigned pull_grid = gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 8);
-    switch (kernels::pull_variant()) {
-      case 0:
-        kernels::pull_step_kernel<false><<<pull_grid, 256, 0, stream>>>(in_adj, op, cur.data(), nxt.data(),
-                                                                         D.visited.data(), scratch.d);
-        break;
-      case 2:
-        kernels::pull_step_staged_kernel<<<pull_grid, 256, 0, stream>>>(in_adj, op, cur.data(), nxt.data(),
-                                                                        D.visited.data(), scratch.d);
-        break;
-      default:
-        kernels::pull_step_kernel<true><<<pull_grid, 256, 0, stream>>>(in_adj, op, cur.data(), nxt.data(),
-                                                                        D.visited.data(), scratch.d);
-    }
+    kernels::pull_step_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 6), 256, 0, stream>>>(
+        in_adj, op, cur.data(), nxt.data(), D.visited.data(), scratch.d);
     prof.end(stream);
     error::check_last("pull step");
     scratch.fetch(stream);
@@ -346,6 +334,12 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
 }
 
 }  // namespace detail
+
+/// Pairs a push operator with its bottom-up form for direction-optimised advance (see pull.cuh).
+template <typename push_t, typename pull_t>
+kernels::directional_operator_t<push_t, pull_t> directional(push_t push, pull_t pull) {
+  return kernels::directional_operator_t<push_t, pull_t>{push, pull};
+}
 
 /**
  * @brief Explicit-buffers form (reference advance.hxx:91-129; used by e.g. bc.hxx:140-146).

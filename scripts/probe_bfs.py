@@ -37,8 +37,6 @@ runs = [(v, pv, int(h), float(a), float(b)) for (v, pv) in runs for h in args.hi
 for variant, pv, hints, alpha, beta in runs:
     lb, direction = variant.split(":")
     ess.tune("pull_hints", hints)
-    if pv is not None:
-        ess.tune("pull_variant", pv)
     variant = f"{variant}/pv{pv}/h{hints}/a{alpha:g}/b{beta:g}"
     for s in srcs:
         ctx.profile(True)
