@@ -57,6 +57,9 @@ _SIGNATURES = {
     "ess_graph_create": (c_int, [c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                  c_void_p, POINTER(c_void_p)]),
     "ess_graph_destroy": (c_int, [c_void_p]),
+    "ess_graph_build_pull_hints": (c_int, [c_void_p, c_void_p]),
+    "ess_bfs_partition_pull": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p]),
     "ess_transpose_csr": (c_int, [c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ess_bfs": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int, c_int, c_float, c_float, POINTER(RunInfo)]),
     "ess_sssp": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int, POINTER(RunInfo)]),
@@ -71,9 +74,11 @@ _SIGNATURES = {
                                  c_int32]),
     "ess_frontier_to_bitmap": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]),
     "ess_bitmap_to_frontier": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_int64)]),
-    "ess_bfs_partition_step": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
-    "ess_bfs_absorb": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
-                               POINTER(c_int64), POINTER(c_int64)]),
+    "ess_bits_to_list_async": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "ess_bfs_partition_step": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_int64]),
+    "ess_bfs_absorb": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int64, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -174,7 +179,8 @@ class Graph:
     """graph_t view over caller-owned CSR (+ optional CSC) device arrays
     (graph::build::from_csr, reference include/gunrock/graph/build.hxx:21-36)."""
 
-    def __init__(self, csr, csc=None, symmetric: bool | None = None):
+    def __init__(self, csr, csc=None, symmetric: bool | None = None, partition: bool = False):
+        """partition=True: `csr` is a row range of a partitioned symmetric graph (global column ids)."""
         _need_cuda(csr.offsets, csr.indices, csr.values)
         self.csr, self.csc = csr, csc
         self.n, self.m = int(csr.offsets.numel() - 1), int(csr.indices.numel())
@@ -185,12 +191,16 @@ class Graph:
             assert csc.offsets.dtype == csr.offsets.dtype
         h = c_void_p()
         _check(lib().ess_graph_create(self.n, self.m, self.offset_bits, _p(csr.offsets), _p(csr.indices),
-                                      _p(csr.values), int(sym and csc is None),
+                                      _p(csr.values), (2 if partition else 1) if (sym and csc is None) else 0,
                                       _p(csc.offsets) if csc is not None else None,
                                       _p(csc.indices) if csc is not None else None,
                                       _p(csc.values) if csc is not None else None, byref(h)), "ess_graph_create")
         self.handle = h
         self.has_csc = sym or csc is not None
+
+    def build_pull_hints(self, degree_of_id=None):
+        """graph::build::pull_hints; degree_of_id (int32 per global id) is required for partitions."""
+        _check(lib().ess_graph_build_pull_hints(self.handle, _p(degree_of_id)), "ess_graph_build_pull_hints")
 
     def close(self):
         if getattr(self, "handle", None):

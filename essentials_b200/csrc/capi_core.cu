@@ -123,17 +123,30 @@ int ess_graph_create(int64_t n, int64_t m, int offset_bits, const void* d_row_of
   else
     h->g32 = graph::build::from_csr_and_csc<int32_t, int32_t, float>(
         int32_t(n), int32_t(m), (int32_t*)d_row_offsets, J, X, (int32_t*)t_off, I, Xt);
-  if (h->has_csc && n > 0 && m > 0) {  // acceleration structure of the bottom-up advance, once per graph
-    h->hint_head.resize(std::size_t(n));
-    if (offset_bits == 64) {
-      h->hint_edge64.resize(std::size_t(n));
-      graph::build::pull_hints(h->g64, h->hint_head.data(), h->hint_edge64.data());
-    } else {
-      h->hint_edge32.resize(std::size_t(n));
-      graph::build::pull_hints(h->g32, h->hint_head.data(), h->hint_edge32.data());
+  if (h->has_csc && symmetric != 2 && n > 0 && m > 0) {
+    int rc = ess_graph_build_pull_hints(h, nullptr);  // acceleration structure of bottom-up advance, once per graph
+    if (rc) {
+      delete h;
+      return rc;
     }
   }
   *out = h;
+  return 0;
+  ESS_CATCH
+}
+
+int ess_graph_build_pull_hints(ess_graph_t h, const int32_t* d_degree_of_id) {
+  ESS_TRY
+  if (!h || !h->has_csc) return ess::fail("ess_graph_build_pull_hints: graph has no CSC view");
+  if (h->n <= 0 || h->m <= 0) return 0;
+  h->hint_head.resize(std::size_t(h->n));
+  if (h->offset_bits == 64) {
+    h->hint_edge64.resize(std::size_t(h->n));
+    graph::build::pull_hints(h->g64, h->hint_head.data(), h->hint_edge64.data(), 0, d_degree_of_id);
+  } else {
+    h->hint_edge32.resize(std::size_t(h->n));
+    graph::build::pull_hints(h->g32, h->hint_head.data(), h->hint_edge32.data(), 0, d_degree_of_id);
+  }
   return 0;
   ESS_CATCH
 }
@@ -202,6 +215,20 @@ int ess_bitmap_to_frontier(ess_context_t ctx, const uint32_t* d_words, int64_t u
   error::check_last("ess_bitmap_to_frontier");
   scratch.fetch(stream);
   if (out_count) *out_count = int64_t(scratch.h[gcuda::scratch_t::out_count]);
+  return 0;
+  ESS_CATCH
+}
+
+int ess_bits_to_list_async(ess_context_t ctx, const uint32_t* d_words, int64_t universe, int32_t* d_list) {
+  ESS_TRY
+  auto* c = ctx->single();
+  auto stream = c->stream();
+  auto& scratch = c->scratch();
+  const std::size_t words = (std::size_t(universe) + 31) / 32;
+  scratch.zero(stream);  // the slot counter is left dirty on purpose: the next operator's zero() clears it
+  frontier::kernels::gather_bits_kernel<<<gcuda::persistent_grid(*c, (words + 255) / 256, 8), 256, 0, stream>>>(
+      d_words, words, d_list, scratch.d + gcuda::scratch_t::out_count);
+  error::check_last("ess_bits_to_list_async");
   return 0;
   ESS_CATCH
 }

@@ -80,95 +80,102 @@ int filter_probe(ess_context_t ctx, graph_t& G, const int32_t* d_in, int64_t siz
 
 // ---- multi-GPU BFS level kernels (bitmaps are global, rows are local) -------------------------------
 
-/// Bottom-up over owned rows: owned vertex v (global id row_begin+v) not yet visited joins the candidates
-/// when one of its in-neighbours is in the global frontier bitmap.
+/// Owner side: candidate word = OR of `n_slices` contributions (stride `slice_stride` words); fresh =
+/// candidate & ~visited over the owned words; depth, visited, next-frontier slice, sparse list of fresh local
+/// ids, and the two Beamer counters (|fresh|, Σdeg fresh) accumulated into `counts` (device, caller-zeroed).
 template <typename edge_t>
 __global__ void __launch_bounds__(256)
-    partition_pull_kernel(const graph::adjacency_t<int32_t, edge_t, float> A, long long row_begin,
-                          const unsigned* __restrict__ frontier_bits, const unsigned* __restrict__ visited_bits,
-                          unsigned* __restrict__ candidate_bits) {
+    absorb_kernel(const edge_t* __restrict__ offsets, unsigned n_local, unsigned first_word, int level,
+                  const unsigned* __restrict__ candidates, int n_slices, unsigned slice_stride,
+                  unsigned* __restrict__ visited_bits, unsigned* __restrict__ next_slice, int* __restrict__ depth_local,
+                  int* __restrict__ fresh_list, b200::counter_t* counts) {
   const unsigned lane = b200::lane_id();
-  const std::size_t n_words = (std::size_t(A.n) + 31) / 32;
-  const std::size_t first_word = std::size_t(row_begin) >> 5;
-  const std::size_t warps = (std::size_t(gridDim.x) * blockDim.x) >> 5;
-  for (std::size_t w = (std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
+  const unsigned n_words = (n_local + 31u) >> 5;
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  b200::counter_t edges = 0;
+  for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
     const unsigned seen = visited_bits[first_word + w];
-    bool found = false;
-    const std::size_t v = w * 32 + lane;
-    if (seen != 0xffffffffu && !((seen >> lane) & 1u) && v < std::size_t(A.n)) {
-      for (edge_t e = A.offsets[v], end = A.offsets[v + 1]; e < end; ++e) {
-        const unsigned u = unsigned(__ldg(A.indices + e));
-        if ((__ldg(frontier_bits + (u >> 5)) >> (u & 31u)) & 1u) {
-          found = true;
-          break;
-        }
-      }
-    }
-    const unsigned fresh = __ballot_sync(b200::full_mask, found);
-    if (lane == 0) candidate_bits[first_word + w] = fresh;
-  }
-}
-
-/// Owner side: fresh = candidate & ~visited over the owned words; depth, visited, next frontier, counters.
-template <typename edge_t>
-__global__ void __launch_bounds__(256)
-    absorb_kernel(const edge_t* __restrict__ offsets, long long n_local, long long row_begin, int level,
-                  const unsigned* __restrict__ candidate_bits, unsigned* __restrict__ visited_bits,
-                  unsigned* __restrict__ next_bits, int* __restrict__ depth_local, b200::counter_t* counters) {
-  const unsigned lane = b200::lane_id();
-  const std::size_t n_words = (std::size_t(n_local) + 31) / 32;
-  const std::size_t first_word = std::size_t(row_begin) >> 5;
-  const std::size_t warps = (std::size_t(gridDim.x) * blockDim.x) >> 5;
-  b200::counter_t vertices = 0, edges = 0;
-  for (std::size_t w = (std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
-    const unsigned seen = visited_bits[first_word + w];
-    const unsigned fresh = candidate_bits[first_word + w] & ~seen;
+    unsigned cand = 0;
+    for (int p = 0; p < n_slices; ++p) cand |= candidates[std::size_t(p) * slice_stride + w];
+    const unsigned fresh = cand & ~seen;
     if (lane == 0) {
-      next_bits[first_word + w] = fresh;
+      next_slice[w] = fresh;
       if (fresh) visited_bits[first_word + w] = seen | fresh;
-      vertices += __popc(fresh);
     }
-    const std::size_t v = w * 32 + lane;
-    if (((fresh >> lane) & 1u) && v < std::size_t(n_local)) {
+    if (fresh == 0) continue;  // warp-uniform
+    b200::counter_t at = 0;
+    if (lane == 0) at = atomicAdd(counts, b200::counter_t(__popc(fresh)));
+    at = __shfl_sync(b200::full_mask, at, 0);
+    const unsigned v = (w << 5) + lane;
+    if (((fresh >> lane) & 1u) && v < n_local) {
       depth_local[v] = level;
+      fresh_list[at + __popc(fresh & b200::lanes_below(lane))] = int(v);
       edges += b200::counter_t(offsets[v + 1] - offsets[v]);
     }
   }
   edges = b200::warp_sum(edges);
-  if (lane == 0) {
-    if (vertices) atomicAdd(counters + scratch_t::out_count, vertices);
-    if (edges) atomicAdd(counters + scratch_t::aux2, edges);
+  if (lane == 0 && edges) atomicAdd(counts + 1, edges);
+}
+
+inline int fail_pull_via_step() {
+  return ess::fail("ess_bfs_partition_step: bottom-up levels go through ess_bfs_partition_pull");
+}
+
+/// Copies (out_count, aux2) of the operator counter block into the caller's two int64 and re-zeroes the block.
+static __global__ void export_counts_kernel(b200::counter_t* counters, b200::counter_t* counts) {
+  if (threadIdx.x == 0) {
+    counts[0] += counters[scratch_t::out_count];
+    counts[1] += counters[scratch_t::aux2];
   }
+  if (threadIdx.x < scratch_t::n_slots) counters[threadIdx.x] = 0;
+}
+
+template <typename graph_t>
+int partition_pull(ess_context_t ctx, graph_t& G, int64_t row_begin, int32_t level, const uint32_t* d_frontier_bits,
+                   uint32_t* d_visited_bits, uint32_t* d_next_slice, int32_t* d_depth_local, int64_t* d_counts) {
+  auto* c = ctx->single();
+  auto stream = c->stream();
+  auto& scratch = c->scratch();
+  auto A = graph::adjacency_of<true>(G);  // symmetric graph: the CSC view aliases the owned CSR rows (+ hints)
+  int32_t* depth = d_depth_local;
+  using edge_t = typename graph_t::edge_type;
+  // the destination is an owned, unvisited vertex handled by exactly one thread: adopting it is a plain store
+  auto adopt = [depth, level] __device__(int32_t const& src, int32_t const& dst_local, edge_t const& e,
+                                         float const& w) -> bool {
+    depth[dst_local] = level;
+    return true;
+  };
+  scratch.zero(stream);
+  c->profiler().begin(gcuda::profiler_t::pull_step, stream);
+  operators::advance::kernels::pull_step_kernel<<<gcuda::persistent_grid(*c, (std::size_t(A.n) + 255) / 256, 6), 256,
+                                                  0, stream>>>(A, adopt, d_frontier_bits, d_next_slice,
+                                                               d_visited_bits + (row_begin >> 5), scratch.d);
+  export_counts_kernel<<<1, 32, 0, stream>>>(scratch.d, reinterpret_cast<b200::counter_t*>(d_counts));
+  c->profiler().end(stream, 2);
+  scratch.clean = true;  // export_counts_kernel re-zeroed the block
+  error::check_last("partition pull");
+  return 0;
 }
 
 template <typename graph_t>
 int partition_step(ess_context_t ctx, graph_t& G, int64_t row_begin, int64_t n_global, int pull,
-                   const uint32_t* d_frontier_bits, const uint32_t* d_visited_bits, uint32_t* d_candidate_bits) {
+                   const uint32_t* d_frontier_bits, const uint32_t* d_visited_bits, uint32_t* d_candidate_bits,
+                   const int32_t* d_frontier_list, int64_t frontier_count) {
   using edge_t = typename graph_t::edge_type;
   auto* c = ctx->single();
   auto stream = c->stream();
   const auto A = graph::adjacency_of<false>(G);
   const std::size_t n_local = std::size_t(A.n);
-  if (pull) {
-    partition_pull_kernel<edge_t><<<gcuda::persistent_grid(*c, (n_local + 255) / 256, 8), 256, 0, stream>>>(
-        A, (long long)row_begin, d_frontier_bits, d_visited_bits, d_candidate_bits);
-    error::check_last("partition pull");
-    return 0;
-  }
-  // push: owned slice of the frontier bitmap -> list of local row ids -> balanced advance whose operator
-  // ORs unvisited neighbours into the (global) candidate bitmap.
-  auto& scratch = c->scratch();
-  borrowed_frontier_t<edge_t> in, out;
-  in.reserve(n_local);
-  scratch.zero(stream);
-  const std::size_t words = (n_local + 31) / 32;
-  frontier::kernels::gather_bits_kernel<<<gcuda::persistent_grid(*c, (words + 255) / 256, 8), 256, 0, stream>>>(
-      d_frontier_bits + (std::size_t(row_begin) >> 5), words, in.data(), scratch.d + scratch_t::out_count);
-  scratch.fetch(stream);
-  in.count = std::size_t(scratch.h[scratch_t::out_count]);
+  if (pull) return fail_pull_via_step();
+  // push: balanced advance over this rank's sparse frontier (local row ids); the operator ORs unvisited
+  // neighbours into the global-length candidate bitmap. No host round trip: the caller synchronises once per
+  // level through the all_gather that follows.
   cudaMemsetAsync(d_candidate_bits, 0, ((std::size_t(n_global) + 31) / 32) * sizeof(uint32_t), stream);
-  if (!in.count) return 0;
-  memory::device_array_t<edge_t> segments;
+  if (frontier_count <= 0) return 0;
+  borrowed_frontier_t<edge_t> in, out;
+  in.ptr = const_cast<int32_t*>(d_frontier_list);
+  in.count = in.cap = std::size_t(frontier_count);
+  static thread_local memory::device_array_t<edge_t> segments;  // merge-path work offsets, reused across levels
   const unsigned* visited = d_visited_bits;
   unsigned* candidate = d_candidate_bits;
   auto op = [visited, candidate] __device__(int32_t const& src, int32_t const& nbr, edge_t const& e,
@@ -178,8 +185,12 @@ int partition_step(ess_context_t ctx, graph_t& G, int64_t row_begin, int64_t n_g
     return false;
   };
   using namespace operators;
-  advance::execute<load_balance_t::bucketing, advance_direction_t::forward, advance_io_type_t::vertices,
+  auto& scratch = c->scratch();
+  const bool was_async = scratch.async_when_no_output;
+  scratch.async_when_no_output = true;
+  advance::execute<load_balance_t::merge_path, advance_direction_t::forward, advance_io_type_t::vertices,
                    advance_io_type_t::none>(G, op, &in, &out, segments, *ctx->ctx);
+  scratch.async_when_no_output = was_async;
   return 0;
 }
 
@@ -231,40 +242,52 @@ int ess_filter_probe(ess_context_t ctx, ess_graph_t g, int alg, const int32_t* d
 
 int ess_bfs_partition_step(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int64_t n_global, int pull,
                            const uint32_t* d_frontier_bits, const uint32_t* d_visited_bits,
-                           uint32_t* d_candidate_bits) {
+                           uint32_t* d_candidate_bits, const int32_t* d_frontier_list, int64_t frontier_count) {
   ESS_TRY
   if (!ctx || !g) return ess::fail("ess_bfs_partition_step: null argument");
   if (row_begin % 32) return ess::fail("ess_bfs_partition_step: row_begin must be a multiple of 32");
   ESS_WITH_GRAPH(g, G, {
-    return partition_step(ctx, G, row_begin, n_global, pull, d_frontier_bits, d_visited_bits, d_candidate_bits);
+    return partition_step(ctx, G, row_begin, n_global, pull, d_frontier_bits, d_visited_bits, d_candidate_bits,
+                          d_frontier_list, frontier_count);
   })
   ESS_CATCH
 }
 
-int ess_bfs_absorb(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int64_t n_global, int32_t level,
-                   const uint32_t* d_candidate_bits, uint32_t* d_visited_bits, uint32_t* d_next_bits,
-                   int32_t* d_depth_local, int64_t* fresh_vertices, int64_t* fresh_edges) {
+int ess_bfs_partition_pull(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int32_t level,
+                           const uint32_t* d_frontier_bits, uint32_t* d_visited_bits, uint32_t* d_next_slice,
+                           int32_t* d_depth_local, int64_t* d_counts) {
   ESS_TRY
-  if (!ctx || !g) return ess::fail("ess_bfs_absorb: null argument");
+  if (!ctx || !g || !d_counts) return ess::fail("ess_bfs_partition_pull: null argument");
+  if (row_begin % 32) return ess::fail("ess_bfs_partition_pull: row_begin must be a multiple of 32");
+  if (!g->has_csc) return ess::fail("ess_bfs_partition_pull: the partition must be created symmetric (CSC view)");
+  ESS_WITH_GRAPH(g, G, {
+    return partition_pull(ctx, G, row_begin, level, d_frontier_bits, d_visited_bits, d_next_slice, d_depth_local,
+                          d_counts);
+  })
+  ESS_CATCH
+}
+
+int ess_bfs_absorb(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int32_t level, const uint32_t* d_candidates,
+                   int32_t n_slices, int64_t slice_stride_words, uint32_t* d_visited_bits, uint32_t* d_next_slice,
+                   int32_t* d_depth_local, int32_t* d_fresh_list, int64_t* d_counts) {
+  ESS_TRY
+  if (!ctx || !g || !d_candidates || !d_counts) return ess::fail("ess_bfs_absorb: null argument");
   auto* c = ctx->single();
   auto stream = c->stream();
-  auto& scratch = c->scratch();
-  scratch.zero(stream);
-  const std::size_t n_local = std::size_t(g->n);
-  const unsigned grid = gcuda::persistent_grid(*c, (n_local + 255) / 256, 8);
+  const unsigned n_local = unsigned(g->n);
+  const unsigned grid = gcuda::persistent_grid(*c, (std::size_t(n_local) + 255) / 256, 8);
+  auto* counts = reinterpret_cast<b200::counter_t*>(d_counts);
+  c->profiler().begin(gcuda::profiler_t::dense_state, stream);
   if (g->offset_bits == 64)
-    absorb_kernel<int64_t><<<grid, 256, 0, stream>>>(g->g64.get_row_offsets(), (long long)n_local, (long long)row_begin,
-                                                      level, d_candidate_bits, d_visited_bits, d_next_bits,
-                                                      d_depth_local, scratch.d);
+    absorb_kernel<int64_t><<<grid, 256, 0, stream>>>(g->g64.get_row_offsets(), n_local, unsigned(row_begin >> 5), level,
+                                                      d_candidates, n_slices, unsigned(slice_stride_words),
+                                                      d_visited_bits, d_next_slice, d_depth_local, d_fresh_list, counts);
   else
-    absorb_kernel<int32_t><<<grid, 256, 0, stream>>>(g->g32.get_row_offsets(), (long long)n_local, (long long)row_begin,
-                                                      level, d_candidate_bits, d_visited_bits, d_next_bits,
-                                                      d_depth_local, scratch.d);
+    absorb_kernel<int32_t><<<grid, 256, 0, stream>>>(g->g32.get_row_offsets(), n_local, unsigned(row_begin >> 5), level,
+                                                      d_candidates, n_slices, unsigned(slice_stride_words),
+                                                      d_visited_bits, d_next_slice, d_depth_local, d_fresh_list, counts);
+  c->profiler().end(stream);
   error::check_last("absorb");
-  scratch.fetch(stream);
-  if (fresh_vertices) *fresh_vertices = int64_t(scratch.h[scratch_t::out_count]);
-  if (fresh_edges) *fresh_edges = int64_t(scratch.h[scratch_t::aux2]);
-  (void)n_global;
   return 0;
   ESS_CATCH
 }

@@ -31,39 +31,50 @@ INF = 2**31 - 1
 
 
 class CudaBackend:
-    """Local level kernels of one rank, in libessentials_b200.so."""
+    """Local level kernels of one rank, in libessentials_b200.so. Both calls only enqueue work."""
 
     def __init__(self, csr_local, row_begin: int, n_global: int, device, stream):
         import essentials_b200 as ess
         self.ess = ess
         self.ctx = ess.Context(device.index, stream=stream)
-        self.graph = ess.Graph(csr_local, symmetric=True)
+        self.graph = ess.Graph(csr_local, symmetric=True, partition=True)
         self.row_begin, self.n_global = row_begin, n_global
+        # bottom-up hints need the degree of remote neighbours: gather all degrees once at setup
+        deg_local = (csr_local.offsets[1:] - csr_local.offsets[:-1]).to(torch.int32).contiguous()
+        deg_global = torch.empty(n_global, dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(deg_global, deg_local)
+        self.graph.build_pull_hints(deg_global)
+        del deg_global
 
-    def step(self, pull: bool, frontier_bits, visited_bits, candidate_bits):
+    def step(self, pull: bool, frontier_bits, visited_bits, candidate_bits, frontier_list, frontier_count: int):
         ess = self.ess
         ess._check(ess.lib().ess_bfs_partition_step(self.ctx.handle, self.graph.handle, self.row_begin, self.n_global,
                                                     int(pull), ess._p(frontier_bits), ess._p(visited_bits),
-                                                    ess._p(candidate_bits)), "ess_bfs_partition_step")
+                                                    ess._p(candidate_bits), ess._p(frontier_list),
+                                                    int(frontier_count)), "ess_bfs_partition_step")
 
-    def absorb(self, level: int, candidate_bits, visited_bits, next_bits, depth_local):
+    def pull(self, level: int, frontier_bits, visited_bits, next_slice, depth_local, counts):
         ess = self.ess
-        fv, fe = c_int64(0), c_int64(0)
-        ess._check(ess.lib().ess_bfs_absorb(self.ctx.handle, self.graph.handle, self.row_begin, self.n_global, level,
-                                            ess._p(candidate_bits), ess._p(visited_bits), ess._p(next_bits),
-                                            ess._p(depth_local), byref(fv), byref(fe)), "ess_bfs_absorb")
-        return fv.value, fe.value
+        ess._check(ess.lib().ess_bfs_partition_pull(self.ctx.handle, self.graph.handle, self.row_begin, level,
+                                                    ess._p(frontier_bits), ess._p(visited_bits), ess._p(next_slice),
+                                                    ess._p(depth_local), ess._p(counts)), "ess_bfs_partition_pull")
+
+    def gather_fresh(self, next_slice, fresh_list):
+        """Sparse list (local row ids) of the bits of the owned next-frontier slice; enqueue only."""
+        ess = self.ess
+        ess._check(ess.lib().ess_bits_to_list_async(self.ctx.handle, ess._p(next_slice), int(next_slice.numel()) * 32,
+                                                    ess._p(fresh_list)), "ess_bits_to_list_async")
+
+    def absorb(self, level: int, candidates, n_slices: int, stride_words: int, visited_bits, next_slice, depth_local,
+               fresh_list, counts):
+        ess = self.ess
+        ess._check(ess.lib().ess_bfs_absorb(self.ctx.handle, self.graph.handle, self.row_begin, level,
+                                            ess._p(candidates), n_slices, stride_words, ess._p(visited_bits),
+                                            ess._p(next_slice), ess._p(depth_local), ess._p(fresh_list),
+                                            ess._p(counts)), "ess_bfs_absorb")
 
     def launches(self) -> int:
         return self.ctx.launches()
-
-
-def _or_reduce_rows(t: torch.Tensor) -> torch.Tensor:
-    """Bitwise OR over dim 0 of an int32 matrix."""
-    out = t[0].clone()
-    for i in range(1, t.shape[0]):
-        out.bitwise_or_(t[i])
-    return out
 
 
 class PartitionedBFS:
@@ -71,7 +82,7 @@ class PartitionedBFS:
 
     def __init__(self, csr_local, row_begin: int, n_global: int, rank: int, world: int, backend, device,
                  alpha: float = 14.0, beta: float = 24.0):
-        assert n_global % (32 * world) == 0, "partition boundaries must be multiples of 32 vertices"
+        assert n_global % (64 * world) == 0, "partition boundaries must be multiples of 64 vertices"
         self.rank, self.world, self.device, self.backend = rank, world, device, backend
         self.n_global, self.per = n_global, n_global // world
         self.row_begin = row_begin
@@ -84,9 +95,10 @@ class PartitionedBFS:
         self.frontier_bits = torch.zeros(self.words, **i32)
         self.visited_bits = torch.zeros(self.words + 1, **i32)
         self.candidate_bits = torch.zeros(self.words + 1, **i32)
-        self.next_bits = torch.zeros(self.words + 1, **i32)
         self.depth_local = torch.empty(self.per, **i32)
-        # payload of the per-level all_gather: the owned frontier slice + (|fresh|, Σdeg fresh) as 2 x int64
+        self.fresh_list = torch.zeros(self.per, **i32)  # sparse frontier of this rank (local row ids)
+        # payload of the per-level all_gather: the owned next-frontier slice + (|fresh|, Σdeg fresh) as 2 x int64,
+        # both written by the absorb kernel
         self.send = torch.zeros(self.wper + 4, **i32)
         self.recv = torch.zeros(world * (self.wper + 4), **i32)
         self.a2a_recv = torch.zeros(self.words, **i32)
@@ -108,7 +120,8 @@ class PartitionedBFS:
         return v // self.per
 
     def bfs(self, source: int) -> dict:
-        """Runs one BFS; depths of the owned range end up in self.depth_local. Returns per-run statistics."""
+        """Runs one BFS; depths of the owned range end up in self.depth_local. Returns per-run statistics.
+        One host synchronisation per level: reading the counters that arrive with the all_gather."""
         dev = self.device
         self.visited_bits[: self.words].copy_(self.isolated_bits)
         self.frontier_bits.zero_()
@@ -118,15 +131,20 @@ class PartitionedBFS:
         self.frontier_bits[word] = mask
         self.visited_bits[word] |= mask
         local = torch.zeros(2, dtype=torch.int64, device=dev)
+        my_count = 0
         if self.owner(source) == self.rank:
             self.depth_local[source - self.row_begin] = 0
+            self.fresh_list[0] = source - self.row_begin
+            my_count = 1
             local[0] = 1
             local[1] = self.deg_local[source - self.row_begin]
         dist.all_reduce(local)
         n_f, m_f = (int(x) for x in local.tolist())
         m_u = self.m_global - m_f
         prev_n_f, pulling, level, pulls, exchanged = 0, False, 0, 0, 0
+        list_is_current = True  # fresh_list holds this rank's part of the live frontier
         lo_w, hi_w = self.rank * self.wper, (self.rank + 1) * self.wper
+        next_slice, counts = self.send[: self.wper], self.send[self.wper:]
         while n_f > 0:
             level += 1
             if not pulling:
@@ -134,25 +152,32 @@ class PartitionedBFS:
                     pulling = True
             elif n_f < self.n_global / self.beta and n_f < prev_n_f:
                 pulling = False
-            self.backend.step(pulling, self.frontier_bits, self.visited_bits, self.candidate_bits)
+            counts.zero_()
             if pulling:
+                # owner-only level: the single-GPU pull kernel on the owned rows writes depth, visited and the
+                # next slice itself; nothing to exchange before the all_gather
                 pulls += 1
+                self.backend.pull(level, self.frontier_bits, self.visited_bits, next_slice, self.depth_local, counts)
+                list_is_current = False
             else:
-                # candidate slices go to their owners; the owner ORs the P contributions
+                if not list_is_current:  # previous level was bottom-up: rebuild this rank's sparse frontier
+                    self.backend.gather_fresh(self.frontier_bits[lo_w:hi_w], self.fresh_list)
+                self.backend.step(False, self.frontier_bits, self.visited_bits, self.candidate_bits, self.fresh_list,
+                                  my_count)
+                list_is_current = True
+                # candidate slices go to their owners; the owner ORs the P contributions inside absorb
                 dist.all_to_all_single(self.a2a_recv, self.candidate_bits[: self.words])
-                self.candidate_bits[lo_w:hi_w] = _or_reduce_rows(self.a2a_recv.view(self.world, self.wper))
                 exchanged += (self.world - 1) * self.wper * 4
-            fv, fe = self.backend.absorb(level, self.candidate_bits, self.visited_bits, self.next_bits,
-                                         self.depth_local)
-            self.send[: self.wper].copy_(self.next_bits[lo_w:hi_w])
-            self.send[self.wper:].copy_(torch.tensor([fv, fe], dtype=torch.int64).view(torch.int32))
+                self.backend.absorb(level, self.a2a_recv, self.world, self.wper, self.visited_bits, next_slice,
+                                    self.depth_local, self.fresh_list, counts)
             dist.all_gather_into_tensor(self.recv, self.send)
             exchanged += (self.world - 1) * (self.wper + 4) * 4
             rows = self.recv.view(self.world, self.wper + 4)
             self.frontier_bits.view(self.world, self.wper).copy_(rows[:, : self.wper])
             self.visited_bits[: self.words].bitwise_or_(self.frontier_bits)
-            counts = rows[:, self.wper:].contiguous().view(torch.int64).sum(0).tolist()  # the one host sync
-            prev_n_f, n_f, m_f = n_f, int(counts[0]), int(counts[1])
+            per_rank = rows[:, self.wper:].contiguous().view(torch.int64).cpu()  # the one host sync of the level
+            my_count = int(per_rank[self.rank, 0])
+            prev_n_f, n_f, m_f = n_f, int(per_rank[:, 0].sum()), int(per_rank[:, 1].sum())
             m_u -= m_f
         self.levels, self.pull_levels, self.bytes_exchanged = level, pulls, exchanged
         return {"iterations": level, "pull_steps": pulls, "push_steps": level - pulls,

@@ -80,7 +80,9 @@ ESS_API int ess_profile_read(ess_context_t ctx, double* ms_by_class, int64_t* la
 /* graph::build::from_csr<device, csr[|csc]> (include/gunrock/graph/build.hxx:21-36).
  * d_row_offsets: (n+1) x int32 or int64 (offset_bits = 32|64); d_column_indices: m x int32;
  * d_values: m x float or NULL (weight 1). CSC (in-edges), needed for backward / optimized / pull:
- *   symmetric != 0            -> the CSC view aliases the CSR arrays (undirected graph);
+ *   symmetric = 1             -> the CSC view aliases the CSR arrays (undirected graph);
+ *   symmetric = 2             -> same, but the arrays are a ROW RANGE of a partitioned graph (n rows, global
+ *                                column ids): bottom-up hints are not built here (ess_graph_build_pull_hints);
  *   d_column_offsets != NULL  -> caller-provided transpose (same widths);
  *   otherwise                 -> no CSC view; calls that need it fail with an error. */
 ESS_API int ess_graph_create(int64_t n, int64_t m, int offset_bits, const void* d_row_offsets,
@@ -88,6 +90,11 @@ ESS_API int ess_graph_create(int64_t n, int64_t m, int offset_bits, const void* 
                      const void* d_column_offsets, const int32_t* d_row_indices, const float* d_csc_values,
                      ess_graph_t* out);
 ESS_API int ess_graph_destroy(ess_graph_t g);
+/* (Re)builds the bottom-up hints of graph::build::pull_hints (include/gunrock/graph/build.hxx; no reference
+ * counterpart): per vertex, its highest-degree in-neighbour. d_degree_of_id: degree of every id that may appear
+ * as an in-neighbour (required for symmetric = 2 partitions; NULL = read degrees from the graph's own offsets).
+ * ess_graph_create calls it automatically for symmetric = 1 and for caller-provided CSC arrays. */
+ESS_API int ess_graph_build_pull_hints(ess_graph_t g, const int32_t* d_degree_of_id);
 
 /* CSR -> CSC by counting sort on the device (the transpose the reference performs destructively inside
  * graph/detail/build.hxx:103-110). Output buffers are caller-allocated: (n+1) offsets, m indices, m values
@@ -147,22 +154,39 @@ ESS_API int ess_frontier_to_bitmap(ess_context_t ctx, const int32_t* d_list, int
 ESS_API int ess_bitmap_to_frontier(ess_context_t ctx, const uint32_t* d_words, int64_t universe, int32_t* d_list,
                            int64_t* out_count);
 
+/* As ess_bitmap_to_frontier but only enqueues the kernel (no length is returned: the caller already knows the
+ * population count). */
+ESS_API int ess_bits_to_list_async(ess_context_t ctx, const uint32_t* d_words, int64_t universe, int32_t* d_list);
+
 /* ---- multi-GPU (one process per GPU; 1-D vertex partition; exchange done by the host with NCCL) --------
- * One BFS level on the rows [row_begin, row_begin + local graph n) this rank owns; `g` holds those rows
- * with GLOBAL column ids (symmetric graph). Bitmaps cover all global vertices.
- *   pull = 0: expand the owned vertices that are set in d_frontier_bits; every neighbour not in
- *             d_visited_bits is OR-ed into d_candidate_bits (global length) — the host then exchanges
- *             candidate slices and calls ess_bfs_absorb on the owner.
- *   pull = 1: for every owned vertex not in d_visited_bits, look for an in-neighbour in d_frontier_bits;
- *             found vertices are set in d_candidate_bits (owned slice only, no exchange of candidates needed).
- * ess_bfs_absorb: for owned vertices, fresh = candidate & ~visited; depth[fresh] = level; visited |= fresh;
- * writes fresh into d_next_bits (owned slice) and returns |fresh| and Σdeg(fresh). */
+ * The reference has no counterpart (operators throw on context.size() != 1, advance/advance.hxx:125-128).
+ * `g` holds the rows [row_begin, row_begin + n_local) this rank owns, with GLOBAL column ids (symmetric
+ * graph); bitmaps cover all global vertices; both calls only ENQUEUE work on the context's stream — the caller
+ * synchronises once per level (the all_gather of the next frontier carries the counters).
+ *
+ * ess_bfs_partition_step, one BFS level on the owned rows:
+ *   pull = 0: balanced merge-path advance over d_frontier_list (frontier_count LOCAL row ids); every neighbour
+ *             not in d_visited_bits is OR-ed into d_candidate_bits (global length, zeroed here) — the host then
+ *             exchanges candidate slices (all_to_all) and the owner absorbs them.
+ *   pull = 1: not served here — use ess_bfs_partition_pull.
+ * ess_bfs_absorb, owner side: candidate word w = OR over n_slices of d_candidates[p*slice_stride_words + w];
+ *   fresh = candidate & ~visited; depth[fresh] = level; visited |= fresh; d_next_slice[w] = fresh (owned words
+ *   only); fresh LOCAL ids are appended to d_fresh_list; d_counts[0] += |fresh|, d_counts[1] += sum of their
+ *   degrees (two device int64 the caller zeroes). */
 ESS_API int ess_bfs_partition_step(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int64_t n_global, int pull,
-                           const uint32_t* d_frontier_bits, const uint32_t* d_visited_bits,
-                           uint32_t* d_candidate_bits);
-ESS_API int ess_bfs_absorb(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int64_t n_global, int32_t level,
-                   const uint32_t* d_candidate_bits, uint32_t* d_visited_bits, uint32_t* d_next_bits,
-                   int32_t* d_depth_local, int64_t* fresh_vertices, int64_t* fresh_edges);
+                                   const uint32_t* d_frontier_bits, const uint32_t* d_visited_bits,
+                                   uint32_t* d_candidate_bits, const int32_t* d_frontier_list,
+                                   int64_t frontier_count);
+ /* ess_bfs_partition_pull, one bottom-up level on the owned rows with the single-GPU pull kernel: every owned
+ * vertex outside d_visited_bits that has an in-neighbour in d_frontier_bits gets depth = level, joins visited
+ * and d_next_slice (owned words); d_counts[0] += |fresh|, d_counts[1] += sum of their degrees. */
+ESS_API int ess_bfs_partition_pull(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int32_t level,
+                                   const uint32_t* d_frontier_bits, uint32_t* d_visited_bits,
+                                   uint32_t* d_next_slice, int32_t* d_depth_local, int64_t* d_counts);
+ESS_API int ess_bfs_absorb(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int32_t level,
+                           const uint32_t* d_candidates, int32_t n_slices, int64_t slice_stride_words,
+                           uint32_t* d_visited_bits, uint32_t* d_next_slice, int32_t* d_depth_local,
+                           int32_t* d_fresh_list, int64_t* d_counts);
 
 #ifdef __cplusplus
 }

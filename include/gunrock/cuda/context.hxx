@@ -97,6 +97,9 @@ struct scratch_t {
   inline void fetch(stream_t s);
 
   bool clean = false;
+  /// When set, an advance without an output frontier returns without its host round trip (its caller
+  /// synchronises later, e.g. through a collective): used by the multi-GPU level kernels.
+  bool async_when_no_output = false;
   unsigned long long sequence = 0;  // value the host waits for in h[n_slots]
 };
 

@@ -217,6 +217,8 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
     }
     epilogue(C, out);  // extra kernels that consume the device-side output count before the one sync
     error::check_last("advance launch");
+    if constexpr (!has_output)
+      if (scratch.async_when_no_output) return;  // nothing to report; counters are re-zeroed by the next zero()
     scratch.fetch(stream);
     if constexpr (has_output) {
       if (scratch.h[scratch_t::overflow]) {  // nothing was expanded: grow and go again

@@ -122,6 +122,9 @@ __global__ void __launch_bounds__(256, 6)
     pull_step_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op,
                      const unsigned* __restrict__ frontier_bits, unsigned* __restrict__ next_bits,
                      unsigned* __restrict__ visited, counter_t* counters) {
+  // Multi-GPU use: A may hold only the rows of a contiguous range of global vertices; `visited` and `next_bits`
+  // then point at the words of that range, frontier_bits and the neighbour ids stay global, and the operator
+  // receives the LOCAL row index as destination.
   const unsigned lane = b200::lane_id();
   const unsigned n = unsigned(A.n);
   const unsigned n_words = (n + 31u) >> 5;

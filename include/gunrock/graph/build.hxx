@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(256)
 template <typename vertex_t, typename edge_t>
 __global__ void __launch_bounds__(256)
     pull_hints_kernel(vertex_t n, const edge_t* __restrict__ in_offsets, const vertex_t* __restrict__ in_indices,
-                      const edge_t* __restrict__ degree_offsets, vertex_t* __restrict__ head,
-                      edge_t* __restrict__ head_edge) {
+                      const edge_t* __restrict__ degree_offsets, const vertex_t* __restrict__ degree_of,
+                      vertex_t* __restrict__ head, edge_t* __restrict__ head_edge) {
   const unsigned lane = threadIdx.x & 31;
   const std::size_t warps = (std::size_t(gridDim.x) * blockDim.x) >> 5;
   for (std::size_t v = (std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; v < std::size_t(n); v += warps) {
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256)
     edge_t best_edge = e;
     for (edge_t k = b + lane; k < e; k += 32) {
       const vertex_t u = in_indices[k];
-      const long long d = (long long)(degree_offsets[u + 1] - degree_offsets[u]);
+      const long long d = degree_of ? (long long)degree_of[u] : (long long)(degree_offsets[u + 1] - degree_offsets[u]);
       if (d > best_deg) {  // strict: keeps the earliest edge of this lane on ties
         best_deg = d;
         best_edge = k;
@@ -208,7 +208,9 @@ auto from_csr(vertex_t const& r, vertex_t const& c, edge_t const& nnz, edge_t* A
  */
 template <typename graph_type>
 void pull_hints(graph_type& G, typename graph_type::vertex_type* head, typename graph_type::edge_type* head_edge,
-                cudaStream_t stream = 0) {
+                cudaStream_t stream = 0, const typename graph_type::vertex_type* degree_of = nullptr) {
+  // degree_of (optional): degree of every vertex id that can appear as an in-neighbour. Needed when G holds
+  // only a row range of a partitioned graph, whose offsets cannot answer degree queries for remote ids.
   using csr_v = typename graph_type::graph_csr_view_t;
   using csc_v = typename graph_type::graph_csc_view_t;
   static_assert(graph_type::template contains_representation<csc_v>(), "pull hints belong to the CSC view");
@@ -221,7 +223,7 @@ void pull_hints(graph_type& G, typename graph_type::vertex_type* head, typename 
   const auto n = c.get_number_of_vertices();
   if (n > 0)
     detail::pull_hints_kernel<<<2048, 256, 0, stream>>>(n, c.get_column_offsets(), c.get_row_indices(), degree_offsets,
-                                                        head, head_edge);
+                                                        degree_of, head, head_edge);
   error::throw_if_exception(cudaStreamSynchronize(stream), "pull_hints");
   c.set_pull_hints(head, head_edge);
 }

@@ -30,34 +30,62 @@ class NumpyBackend:
         packed = np.packbits(flags, bitorder="little").view(np.int32)
         words[lo_word:lo_word + packed.size] = torch.from_numpy(packed.copy())
 
-    def step(self, pull, frontier_bits, visited_bits, candidate_bits):
+    def pull(self, level, frontier_bits, visited_bits, next_slice, depth_local, counts):
         n, lo = self.n_global, self.row_begin
         frontier, visited = self._bits(frontier_bits, n), self._bits(visited_bits, n)
-        if pull:
-            found = np.zeros(self.n_local, bool)
-            for v in range(self.n_local):
-                if not visited[lo + v]:
-                    nb = self.col[self.off[v]:self.off[v + 1]]
-                    found[v] = frontier[nb].any()
-            self._store(candidate_bits, found, lo // 32)
+        found = np.zeros(self.n_local, bool)
+        for v in range(self.n_local):
+            if not visited[lo + v]:
+                nb = self.col[self.off[v]:self.off[v + 1]]
+                found[v] = frontier[nb].any()
+        ids = np.nonzero(found)[0]
+        depth_local[torch.from_numpy(ids)] = level
+        visited[lo:lo + self.n_local] |= found
+        self._store(visited_bits, visited, 0)
+        self._store(next_slice, found, 0)
+        deg = np.diff(self.off)
+        counts.view(torch.int64)[0] += int(found.sum())
+        counts.view(torch.int64)[1] += int(deg[found].sum())
+
+    def gather_fresh(self, next_slice, fresh_list):
+        ids = np.nonzero(self._bits(next_slice, self.n_local))[0]
+        fresh_list[: ids.size] = torch.from_numpy(ids.astype(np.int32))
+
+    def step(self, pull, frontier_bits, visited_bits, candidate_bits, frontier_list, frontier_count):
+        n, lo = self.n_global, self.row_begin
+        frontier, visited = self._bits(frontier_bits, n), self._bits(visited_bits, n)
+        assert not pull
+        if False:
+            pass
         else:
             cand = np.zeros(n, bool)
-            for v in np.nonzero(frontier[lo:lo + self.n_local])[0]:
+            mine = frontier_list.numpy()[:frontier_count]
+            assert sorted(mine.tolist()) == np.nonzero(frontier[lo:lo + self.n_local])[0].tolist(), \
+                "sparse list and frontier bitmap of a rank must describe the same set"
+            for v in mine:
                 nb = self.col[self.off[v]:self.off[v + 1]]
                 cand[nb[~visited[nb]]] = True
             self._store(candidate_bits, cand, 0)
 
-    def absorb(self, level, candidate_bits, visited_bits, next_bits, depth_local):
+    def absorb(self, level, candidates, n_slices, stride_words, visited_bits, next_slice, depth_local, fresh_list,
+               counts):
         n, lo = self.n_global, self.row_begin
-        cand = self._bits(candidate_bits, n)[lo:lo + self.n_local]
+        c = candidates.numpy()
+        words = np.zeros((self.n_local + 31) // 32, np.int32)
+        for p in range(n_slices):
+            words |= c[p * stride_words:p * stride_words + words.size]
+        cand = np.unpackbits(words.view(np.uint8), bitorder="little")[: self.n_local].astype(bool)
         visited = self._bits(visited_bits, n)
         fresh = cand & ~visited[lo:lo + self.n_local]
-        depth_local[torch.from_numpy(np.nonzero(fresh)[0])] = level
+        ids = np.nonzero(fresh)[0]
+        depth_local[torch.from_numpy(ids)] = level
+        fresh_list[: ids.size] = torch.from_numpy(ids.astype(np.int32))
         visited[lo:lo + self.n_local] |= fresh
         self._store(visited_bits, visited, 0)
-        self._store(next_bits, fresh, lo // 32)
+        self._store(next_slice, fresh, 0)
         deg = np.diff(self.off)
-        return int(fresh.sum()), int(deg[fresh].sum())
+        counts.view(torch.int64)[0] += int(fresh.sum())
+        counts.view(torch.int64)[1] += int(deg[fresh].sum())
 
 
 def _worker(rank, world, port, scale, sources, out):
