@@ -119,9 +119,20 @@ class PartitionedBFS:
     def owner(self, v: int) -> int:
         return v // self.per
 
-    def bfs(self, source: int) -> dict:
+    def bfs(self, source: int, trace: list | None = None) -> dict:
         """Runs one BFS; depths of the owned range end up in self.depth_local. Returns per-run statistics.
-        One host synchronisation per level: reading the counters that arrive with the all_gather."""
+        One host synchronisation per level: reading the counters that arrive with the all_gather.
+        `trace` (development aid): a list that receives (level, phase, host seconds) tuples, with a device
+        synchronisation after every phase."""
+        import time as _time
+
+        def mark(phase, t0):
+            if trace is None:
+                return t0
+            torch.cuda.synchronize() if self.device.type == "cuda" else None
+            t1 = _time.perf_counter()
+            trace.append((level, phase, t1 - t0))
+            return t1
         dev = self.device
         self.visited_bits[: self.words].copy_(self.isolated_bits)
         self.frontier_bits.zero_()
@@ -152,6 +163,7 @@ class PartitionedBFS:
                     pulling = True
             elif n_f < self.n_global / self.beta and n_f < prev_n_f:
                 pulling = False
+            t0 = _time.perf_counter()
             counts.zero_()
             if pulling:
                 # owner-only level: the single-GPU pull kernel on the owned rows writes depth, visited and the
@@ -159,18 +171,23 @@ class PartitionedBFS:
                 pulls += 1
                 self.backend.pull(level, self.frontier_bits, self.visited_bits, next_slice, self.depth_local, counts)
                 list_is_current = False
+                t0 = mark("pull", t0)
             else:
                 if not list_is_current:  # previous level was bottom-up: rebuild this rank's sparse frontier
                     self.backend.gather_fresh(self.frontier_bits[lo_w:hi_w], self.fresh_list)
                 self.backend.step(False, self.frontier_bits, self.visited_bits, self.candidate_bits, self.fresh_list,
                                   my_count)
                 list_is_current = True
+                t0 = mark("push", t0)
                 # candidate slices go to their owners; the owner ORs the P contributions inside absorb
                 dist.all_to_all_single(self.a2a_recv, self.candidate_bits[: self.words])
                 exchanged += (self.world - 1) * self.wper * 4
+                t0 = mark("all_to_all", t0)
                 self.backend.absorb(level, self.a2a_recv, self.world, self.wper, self.visited_bits, next_slice,
                                     self.depth_local, self.fresh_list, counts)
+                t0 = mark("absorb", t0)
             dist.all_gather_into_tensor(self.recv, self.send)
+            t0 = mark("all_gather", t0)
             exchanged += (self.world - 1) * (self.wper + 4) * 4
             rows = self.recv.view(self.world, self.wper + 4)
             self.frontier_bits.view(self.world, self.wper).copy_(rows[:, : self.wper])
@@ -179,6 +196,7 @@ class PartitionedBFS:
             my_count = int(per_rank[self.rank, 0])
             prev_n_f, n_f, m_f = n_f, int(per_rank[:, 0].sum()), int(per_rank[:, 1].sum())
             m_u -= m_f
+            t0 = mark("merge+sync", t0)
         self.levels, self.pull_levels, self.bytes_exchanged = level, pulls, exchanged
         return {"iterations": level, "pull_steps": pulls, "push_steps": level - pulls,
                 "nvlink_bytes_received": exchanged, "enact_ms": 0.0}

@@ -436,32 +436,63 @@ __global__ void __launch_bounds__(cta_threads)
   const long long total = (long long)counters[scratch_t::work_total];
   const long long n_items = (long long)counters[scratch_t::items];
   counter_t fresh_edges = 0;
-  for (long long g0 = (long long)blockIdx.x * tile_edges; g0 < total; g0 += (long long)gridDim.x * tile_edges) {
+  // Each CTA takes a CONTIGUOUS run of 1024-edge slices, so only its first slice needs the binary search on
+  // the scanned offsets (17 dependent L2 round trips at |F| = 120 K while 254 threads wait); every following
+  // slice starts in the segment the previous one ended in and its last segment is found from shared memory.
+  const long long n_tiles = (total + tile_edges - 1) / tile_edges;
+  const long long per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const long long first_tile = (long long)blockIdx.x * per_cta;
+  const long long last_tile = first_tile + per_cta < n_tiles ? first_tile + per_cta : n_tiles;
+  long long j0 = 0;
+  for (long long tile = first_tile; tile < last_tile; ++tile) {
+    const long long g0 = tile * tile_edges;
     const long long g1 = g0 + tile_edges < total ? g0 + tile_edges : total;
-    if (threadIdx.x == 0 || threadIdx.x == 32) {  // two lanes of two warps search the slice ends in parallel
-      const long long key = threadIdx.x == 0 ? g0 : g1 - 1;
-      long long lo = 0, hi = n_items;  // work_seg[lo] <= key < work_seg[hi]
-      while (hi - lo > 1) {
-        const long long mid = (lo + hi) >> 1;
-        if ((long long)work_seg[mid] <= key)
-          lo = mid;
-        else
-          hi = mid;
+    if (tile == first_tile) {
+      if (threadIdx.x == 0) {
+        long long lo = 0, hi = n_items;  // work_seg[lo] <= g0 < work_seg[hi]
+        while (hi - lo > 1) {
+          const long long mid = (lo + hi) >> 1;
+          if ((long long)work_seg[mid] <= g0)
+            lo = mid;
+          else
+            hi = mid;
+        }
+        sm.bcast[0] = lo;
       }
-      sm.bcast[threadIdx.x ? 1 : 0] = lo;
+      __syncthreads();
+      j0 = sm.bcast[0];
     }
-    __syncthreads();
-    const long long j0 = sm.bcast[0];
-    const int n_seg = int(sm.bcast[1] - j0) + 1;  // <= tile_edges because every staged segment is non-empty
-    for (int j = threadIdx.x; j < n_seg; j += cta_threads) {
-      const long long s = (long long)work_seg[j0 + j];
-      sm.src[j] = work_src[j0 + j];
-      sm.beg[j] = work_beg[j0 + j] + edge_t(s < g0 ? g0 - s : 0);  // first segment may start before the slice
-      sm.seg[j] = edge_t(s < g0 ? 0 : s - g0);
+    // stage segments j0, j0+1, ... until one starts at or beyond g1 (at most tile_edges + 1 of them: all but the
+    // first start inside the slice and are non-empty). Threads load candidates in parallel; the count is the
+    // number of staged segments that start before g1.
+    int n_seg = 0;
+    {
+      unsigned mine = 0;
+      for (int j = threadIdx.x; j <= tile_edges; j += cta_threads) {
+        const long long jj = j0 + j;
+        if (jj < n_items) {
+          const long long s = (long long)work_seg[jj];
+          if (s < g1) {
+            sm.src[j] = work_src[jj];
+            sm.beg[j] = work_beg[jj] + edge_t(s < g0 ? g0 - s : 0);  // first segment may start before the slice
+            sm.seg[j] = edge_t(s < g0 ? 0 : s - g0);
+            ++mine;
+          }
+        }
+      }
+      unsigned total_seg;
+      b200::cta_exclusive_sum<cta_threads, unsigned>(mine, total_seg, sm.scan_u);
+      n_seg = int(total_seg);
     }
     __syncthreads();
     expand_tile<has_output, policy>(A, op, sm, n_seg, edge_t(g1 - g0), output, counters, capacity, visited,
                                     fresh_edges);
+    // next slice starts in the last segment of this one if that segment continues past g1, else in the next
+    {
+      const long long last = j0 + n_seg - 1;
+      const long long last_end = (long long)work_seg[last + 1];  // work_seg[n_items] holds the total
+      j0 = last_end > g1 ? last : last + 1;
+    }
     __syncthreads();
   }
   flush_fresh_edges<policy>(fresh_edges, counters);

@@ -138,31 +138,34 @@ __global__ void __launch_bounds__(256, 6)
     edge_t beg, end;
     vertex_t head;
   };
-  auto load_stage = [&](unsigned w) {
-    stage_t s{0xffffffffu, 0, 0, vertex_t(-1)};
-    if (w < n_words) {
-      s.seen = visited[w];
+  auto load_seen = [&](unsigned w) -> unsigned { return w < n_words ? visited[w] : 0xffffffffu; };
+  // row bounds + hint of this lane's vertex of word w — only for lanes whose visited bit is clear, so fully
+  // or mostly visited words (isolated vertices, late levels) cost no row/hint traffic
+  auto load_stage = [&](unsigned w, unsigned seen) {
+    stage_t s{seen, 0, 0, vertex_t(-1)};
+    if (!((seen >> lane) & 1u)) {  // padding lanes of the last word are marked visited by init_visited_kernel
       const unsigned v = (w << 5) + lane;
-      if (v < n) {
-        s.beg = A.offsets[v];
-        s.end = A.offsets[v + 1];
-        if (hinted) s.head = __ldg(A.head + v);
-      }
+      s.beg = A.offsets[v];
+      s.end = A.offsets[v + 1];
+      if (hinted) s.head = __ldg(A.head + v);
     }
     return s;
   };
   auto probe_of = [&](const stage_t& s) -> unsigned {  // frontier word holding the head of this lane's vertex
-    const bool wanted = !((s.seen >> lane) & 1u) && s.head >= 0;
-    return wanted ? __ldg(frontier_bits + (unsigned(s.head) >> 5)) : 0u;
+    return s.head >= 0 ? __ldg(frontier_bits + (unsigned(s.head) >> 5)) : 0u;
   };
 
+  // software pipeline over the warp's words w, w+warps, ...:  visited word 3 trips ahead, row bounds + hint
+  // 2 trips ahead, frontier probe 1 trip ahead
   unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  stage_t cur = load_stage(w);
-  stage_t nxt = load_stage(w + warps);
+  stage_t cur = load_stage(w, load_seen(w));
+  stage_t nxt = load_stage(w + warps, load_seen(w + warps));
+  unsigned seen_far = load_seen(w + 2 * warps);
   unsigned probe = probe_of(cur);
   while (w < n_words) {
-    const stage_t far = load_stage(w + 2 * warps);  // requests for two trips ahead
-    const unsigned probe_next = probe_of(nxt);      // nxt's loads were issued a whole trip ago
+    const unsigned seen_farther = load_seen(w + 3 * warps);
+    const stage_t far = load_stage(w + 2 * warps, seen_far);
+    const unsigned probe_next = probe_of(nxt);
     bool found = false;
     if (!((cur.seen >> lane) & 1u)) {
       ++scanned;
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(256, 6)
     w += warps;
     cur = nxt;
     nxt = far;
+    seen_far = seen_farther;
     probe = probe_next;
   }
   found_edges = b200::warp_sum(found_edges);

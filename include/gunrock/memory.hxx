@@ -43,12 +43,15 @@ class device_pool_t {
     cudaGetDevice(&dev);
     {
       std::lock_guard<std::mutex> lock(mu);
-      auto it = cached.find({dev, rounded});
-      if (it != cached.end() && !it->second.empty()) {
+      // best fit: the smallest cached block of this device that holds the request without wasting more than
+      // half of itself (frontier buffers grow by data-dependent amounts, so exact sizes rarely repeat)
+      for (auto it = cached.lower_bound({dev, rounded}); it != cached.end() && it->first.first == dev; ++it) {
+        if (it->first.second > 2 * rounded + (std::size_t(4) << 20)) break;
+        if (it->second.empty()) continue;
         void* p = it->second.back();
         it->second.pop_back();
-        cached_bytes -= rounded;
-        live[p] = {dev, rounded};
+        cached_bytes -= it->first.second;
+        live[p] = it->first;
         return p;
       }
     }

@@ -43,6 +43,15 @@ for s in [0] + srcs:
         same = bool(torch.equal(want, depth))
         ok &= same
         print(f"src={s} levels={info['iterations']} pull={info['pull_steps']} wall={ms:.2f} ms equal={same}", flush=True)
+trace = []
+runner.bfs(srcs[-1], trace=trace)
+if rank == 0:
+    import collections
+    agg = collections.OrderedDict()
+    for lvl, phase, dt in trace:
+        agg.setdefault(phase, []).append(dt * 1e6)
+    print("phase breakdown (us, per level, synchronised after each phase): " +
+          "; ".join(f"{k}: n={len(v)} avg={sum(v)/len(v):.0f} max={max(v):.0f}" for k, v in agg.items()), flush=True)
 flag = torch.tensor([int(ok)], device=dev)
 dist.broadcast(flag, 0)
 dist.destroy_process_group()
