@@ -135,6 +135,11 @@ template <typename type_t>
 __host__ __device__ inline type_t* raw_pointer_cast(type_t* p) {
   return p;
 }
+/// Fancy pointers (thrust::device_ptr and friends) expose the raw pointer through get().
+template <typename pointer_t, typename = decltype(std::declval<pointer_t>().get())>
+inline auto raw_pointer_cast(pointer_t p) {
+  return p.get();
+}
 
 /**
  * @brief Owning, growable device buffer of trivially-copyable elements. Move-only.

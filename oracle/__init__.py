@@ -255,16 +255,32 @@ def ref_gpu() -> ctypes.CDLL:
         if not have_ref_gpu():
             raise RuntimeError("oracle/_ref/libref_gpu.so missing: run `make -C oracle refgpu` where /root/reference exists")
         R = ctypes.CDLL(_REF_GPU_SO)
-        for name in ("ref_gpu_bfs", "ref_gpu_sssp", "ref_gpu_pr", "ref_gpu_ppr", "ref_gpu_kcore", "ref_gpu_color"):
-            getattr(R, name).restype = c_float
-        R.ref_gpu_bfs.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
-        R.ref_gpu_sssp.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
-        R.ref_gpu_pr.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]
-        R.ref_gpu_ppr.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]
-        R.ref_gpu_kcore.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
-        R.ref_gpu_color.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+        for name, args in _REF_GPU_PROTOS.items():
+            fn = getattr(R, name)
+            fn.restype, fn.argtypes = c_float, args
         _ref_gpu = R
     return _ref_gpu
+
+
+_G = [c_int, c_int, c_void_p, c_void_p, c_void_p]
+_REF_GPU_PROTOS = {
+    "ref_gpu_bfs": _G + [c_int, c_void_p],
+    "ref_gpu_sssp": _G + [c_int, c_void_p],
+    "ref_gpu_pr": _G + [c_float, c_float, c_void_p],
+    "ref_gpu_ppr": _G + [c_int, c_float, c_float, c_void_p],
+    "ref_gpu_kcore": _G + [c_void_p],
+    "ref_gpu_color": _G + [c_void_p],
+}
+
+
+class _Renamed:
+    """Lets ref_gpu_run call refours_* through the ref_gpu_* names."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        return getattr(self._lib, name.replace("ref_gpu_", "refours_"))
 
 
 def _gpu_args(csr):
@@ -277,13 +293,35 @@ def _gpu_args(csr):
             c_void_p(csr.indices.data_ptr()), c_void_p(vals.data_ptr()))
 
 
-def ref_gpu_run(alg: str, csr, *params):
-    """Runs gunrock::<alg>::run of the REFERENCE on the GPU. Returns (result tensor, enact ms)."""
+_REF_ON_OURS_SO = os.path.join(_HERE, "_ref", "libref_algos_on_ours.so")
+_ref_on_ours = None
+
+
+def have_ref_on_ours() -> bool:
+    return os.path.exists(_REF_ON_OURS_SO)
+
+
+def ref_on_ours():
+    """The reference's unmodified algorithm headers compiled against OUR operator headers (oracle/_ref)."""
+    global _ref_on_ours
+    if _ref_on_ours is None:
+        R = ctypes.CDLL(_REF_ON_OURS_SO)
+        proto = ref_gpu.__globals__["_REF_GPU_PROTOS"]
+        for name, args in proto.items():
+            fn = getattr(R, name.replace("ref_gpu_", "refours_"))
+            fn.restype, fn.argtypes = c_float, args
+        _ref_on_ours = R
+    return _ref_on_ours
+
+
+def ref_gpu_run(alg: str, csr, *params, on_ours: bool = False):
+    """Runs gunrock::<alg>::run of the REFERENCE on the GPU (on_ours=True: the reference's algorithm headers on
+    our operators). Returns (result tensor, enact ms)."""
     import torch
     n, m, off, col, val = _gpu_args(csr)
     dev = csr.indices.device
     torch.cuda.synchronize()
-    R = ref_gpu()
+    R = _Renamed(ref_on_ours()) if on_ours else ref_gpu()
     if alg == "bfs":
         out = torch.empty(n, dtype=torch.int32, device=dev)
         ms = R.ref_gpu_bfs(n, m, off, col, val, int(params[0]), c_void_p(out.data_ptr()))

@@ -1,0 +1,58 @@
+// TEST INFRASTRUCTURE ONLY — API-compatibility proof for the drop-in header tree.
+//
+// The REFERENCE's own, UNMODIFIED algorithm headers (include/gunrock/algorithms/{bfs,sssp,pr,ppr,kcore,color}.hxx,
+// included by absolute path from /root/reference) are compiled against THIS repository's include/gunrock tree:
+// every `#include <gunrock/...>` inside them resolves to our headers, so their enactors run on our operators,
+// frontier, graph views, context and atomics. Built by `make -C oracle refonours` into
+// oracle/_ref/libref_algos_on_ours.so; tests/test_gpu_vs_reference_gpu.py runs it next to the all-reference build
+// (libref_gpu.so) and our own clients and requires the same results.
+#include <gunrock/algorithms/algorithms.hxx>
+#include <gunrock/framework/operators/batch/batch.hxx>
+
+#define REF_STR2(x) #x
+#define REF_STR(x) REF_STR2(x)
+#define REF_ALG(name) REF_STR(REF_ALG_DIR/name)
+#include REF_ALG(bfs.hxx)
+#include REF_ALG(sssp.hxx)
+#include REF_ALG(pr.hxx)
+#include REF_ALG(ppr.hxx)
+#include REF_ALG(kcore.hxx)
+#include REF_ALG(color.hxx)
+
+using namespace gunrock;
+using namespace memory;
+
+static auto make_graph(int n, int m, int* off, int* col, float* val) {
+  return graph::build::from_csr<memory_space_t::device, graph::view_t::csr>(n, n, m, off, col, val);
+}
+
+#define REF_GUARD(body)                                        \
+  try {                                                        \
+    body                                                       \
+  } catch (const std::exception& e) {                          \
+    std::fprintf(stderr, "ref_on_ours: %s\n", e.what());       \
+    return -1.f;                                               \
+  }
+
+extern "C" {
+float refours_bfs(int n, int m, int* d_off, int* d_col, float* d_val, int src, int* d_dist) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); thrust::device_vector<int> pred(1);
+            return gunrock::bfs::run(G, src, d_dist, pred.data().get());)
+}
+float refours_sssp(int n, int m, int* d_off, int* d_col, float* d_val, int src, float* d_dist) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); thrust::device_vector<int> pred(1);
+            return gunrock::sssp::run(G, src, d_dist, pred.data().get());)
+}
+float refours_pr(int n, int m, int* d_off, int* d_col, float* d_val, float alpha, float tol, float* d_p) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); return gunrock::pr::run(G, alpha, tol, d_p);)
+}
+float refours_ppr(int n, int m, int* d_off, int* d_col, float* d_val, int seed, float alpha, float eps, float* d_p) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); return gunrock::ppr::run(G, seed, d_p, alpha, eps);)
+}
+float refours_kcore(int n, int m, int* d_off, int* d_col, float* d_val, int* d_k) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); return gunrock::kcore::run(G, d_k);)
+}
+float refours_color(int n, int m, int* d_off, int* d_col, float* d_val, int* d_colors) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); return gunrock::color::run(G, d_colors);)
+}
+}  // extern "C"

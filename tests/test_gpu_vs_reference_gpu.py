@@ -71,3 +71,35 @@ def test_reference_gpu_colouring_is_valid_and_ours_too(ctx, kron):
     ours, _ = ess.color(ctx, g)
     assert oracle.color_errors(off, col, ref_colors.cpu().numpy()) == 0
     assert oracle.color_errors(off, col, ours.cpu().numpy()) == 0
+
+
+# ---- the reference's UNMODIFIED algorithm headers compiled against our operator headers ----------------------
+needs_compat = pytest.mark.skipif(not oracle.have_ref_on_ours(), reason="oracle/_ref/libref_algos_on_ours.so not built")
+
+
+@needs_compat
+def test_reference_algorithm_headers_run_on_our_operators(ctx, kron):
+    """Drop-in proof: reference bfs/sssp/kcore/pr/ppr/color sources + our include tree == all-reference build."""
+    csr, g = kron
+    off, col, val = csr.host()
+    s = gg.pick_sources(csr, 1)[0]
+    ref_bfs, _ = oracle.ref_gpu_run("bfs", csr, s)
+    got, _ = oracle.ref_gpu_run("bfs", csr, s, on_ours=True)
+    assert torch.equal(got, ref_bfs)
+    assert np.array_equal(got.cpu().numpy(), oracle.bfs(off, col, s))
+    ref_sssp, _ = oracle.ref_gpu_run("sssp", csr, s)
+    got, _ = oracle.ref_gpu_run("sssp", csr, s, on_ours=True)
+    assert torch.equal(got, ref_sssp)
+    small = gg.rmat_csr(11, device="cuda")
+    assert torch.equal(oracle.ref_gpu_run("kcore", small, on_ours=True)[0], oracle.ref_gpu_run("kcore", small)[0])
+    got, _ = oracle.ref_gpu_run("ppr", small, 3, 0.15, 1e-6, on_ours=True)
+    want, _ = oracle.ref_gpu_run("ppr", small, 3, 0.15, 1e-6)
+    assert float((got - want).abs().max()) <= 1e-6
+    directed = gg.rmat_csr(12, symmetric=False, weights="ones", device="cuda")
+    got, _ = oracle.ref_gpu_run("pr", directed, 0.85, 1e-6, on_ours=True)
+    want, _ = oracle.ref_gpu_run("pr", directed, 0.85, 1e-6)
+    assert ((got.double() - want.double()).abs().sum() / want.double().sum()).item() < 2e-6
+    o, c, _ = small.host()
+    colors, _ = oracle.ref_gpu_run("color", small, on_ours=True)
+    assert oracle.color_errors(o, c, colors.cpu().numpy()) == 0
+    assert np.array_equal(colors.cpu().numpy(), oracle.color_jacobi(o, c)[0]), "our random stream + deterministic filter"
