@@ -72,6 +72,7 @@ _SIGNATURES = {
                                   POINTER(c_int64), c_void_p, c_int32]),
     "ess_filter_probe": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, POINTER(c_int64), c_void_p,
                                  c_int32]),
+    "ess_uniquify_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_int64)]),
     "ess_frontier_to_bitmap": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]),
     "ess_bitmap_to_frontier": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_int64)]),
     "ess_bits_to_list_async": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
@@ -314,6 +315,16 @@ def filter_probe(ctx: Context, g: Graph, items, alg: str = "predicated", modulus
     _check(lib().ess_filter_probe(ctx.handle, g.handle, FILTER[alg], _p(items), int(items.numel()), _p(out),
                                   byref(n_out), _p(calls), modulus), "ess_filter_probe")
     return out[: n_out.value], calls
+
+
+def uniquify_probe(ctx: Context, g: Graph, items):
+    """operators::uniquify::execute<unique>: ascending duplicate-free valid ids."""
+    import torch
+    out = torch.empty(max(min(int(items.numel()), g.n), 1), dtype=torch.int32, device=items.device)
+    cnt = c_int64(0)
+    _check(lib().ess_uniquify_probe(ctx.handle, g.handle, _p(items), int(items.numel()), _p(out), byref(cnt)),
+           "ess_uniquify_probe")
+    return out[: cnt.value]
 
 
 def frontier_to_bitmap(ctx: Context, items, universe: int):

@@ -251,6 +251,22 @@ int ess_filter_probe(ess_context_t ctx, ess_graph_t g, int alg, const int32_t* d
   ESS_CATCH
 }
 
+int ess_uniquify_probe(ess_context_t ctx, ess_graph_t g, const int32_t* d_in, int64_t size, int32_t* d_out,
+                       int64_t* out_count) {
+  ESS_TRY
+  if (!ctx || !g || !d_out) return ess::fail("ess_uniquify_probe: null argument");
+  using frontier_type = frontier::frontier_t<int32_t, int32_t>;
+  frontier_type in{std::size_t(size), 1.0f};
+  frontier_type out;
+  if (size) cudaMemcpy(in.data(), d_in, std::size_t(size) * sizeof(int32_t), cudaMemcpyDeviceToDevice);
+  operators::uniquify::execute<operators::uniquify_algorithm_t::unique>(&in, &out, std::size_t(g->n), *ctx->ctx);
+  const std::size_t k = out.get_number_of_elements();
+  if (k) cudaMemcpy(d_out, out.data(), k * sizeof(int32_t), cudaMemcpyDeviceToDevice);
+  if (out_count) *out_count = int64_t(k);
+  return 0;
+  ESS_CATCH
+}
+
 int ess_bfs_partition_step(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int64_t n_global, int pull,
                            const uint32_t* d_frontier_bits, const uint32_t* d_visited_bits,
                            uint32_t* d_candidate_bits, const int32_t* d_frontier_list, int64_t frontier_count) {

@@ -146,6 +146,12 @@ ESS_API int ess_advance_probe(ess_context_t ctx, ess_graph_t g, int lb, int dire
 ESS_API int ess_filter_probe(ess_context_t ctx, ess_graph_t g, int alg, const int32_t* d_in, int64_t size, int32_t* d_out,
                      int64_t* out_count, int32_t* d_calls, int32_t modulus);
 
+/* operators::uniquify::execute<unique>(in, out, ctx) — include/gunrock/framework/operators/uniquify/uniquify.hxx:15-72
+ * (sort + unique in the reference; here a sparse->dense->sparse round trip): d_out receives the ascending,
+ * duplicate-free valid ids of d_in (d_out needs min(size, n) elements). */
+ESS_API int ess_uniquify_probe(ess_context_t ctx, ess_graph_t g, const int32_t* d_in, int64_t size, int32_t* d_out,
+                               int64_t* out_count);
+
 /* frontier sparse -> dense (bitmap, 1 bit per vertex; d_words: ceil(universe/32)+1 x uint32) and back
  * (ascending within 1024-vertex groups). Stand for the conversions SURVEY.md K14 R3/R4 lists; the
  * reference's boolmap_frontier_t (frontier/experimental/boolmap_frontier.hxx:25-202) has none. */

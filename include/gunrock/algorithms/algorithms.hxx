@@ -19,6 +19,11 @@
 #include <thrust/transform.h>
 #include <thrust/transform_reduce.h>
 #include <thrust/functional.h>
+#include <thrust/sort.h>
+#include <thrust/sequence.h>
+#include <thrust/reduce.h>
+#include <thrust/logical.h>
+#include <thrust/extrema.h>
 #include <thrust/iterator/counting_iterator.h>
 
 #include <gunrock/memory.hxx>

@@ -314,6 +314,32 @@ def ref_on_ours():
     return _ref_on_ours
 
 
+def ref_on_ours_extra(alg: str, csr, *tensors_and_params):
+    """bc / spmv of the reference's headers on our operators (no all-reference counterpart links: moderngpu)."""
+    import torch
+    n, m, off, col, val = _gpu_args(csr)
+    R = ref_on_ours()
+    dev = csr.indices.device
+    torch.cuda.synchronize()
+    if alg == "bc":
+        out = torch.zeros(n, dtype=torch.float32, device=dev)
+        R.refours_bc.restype = c_float
+        R.refours_bc.argtypes = _G + [c_int, c_void_p]
+        ms = R.refours_bc(n, m, off, col, val, int(tensors_and_params[0]), c_void_p(out.data_ptr()))
+    elif alg == "spmv":
+        x = tensors_and_params[0]
+        out = torch.zeros(n, dtype=torch.float32, device=dev)
+        R.refours_spmv.restype = c_float
+        R.refours_spmv.argtypes = _G + [c_void_p, c_void_p]
+        ms = R.refours_spmv(n, m, off, col, val, c_void_p(x.data_ptr()), c_void_p(out.data_ptr()))
+    else:
+        raise ValueError(alg)
+    torch.cuda.synchronize()
+    if ms < 0:
+        raise RuntimeError(f"reference-on-ours {alg} failed")
+    return out, float(ms)
+
+
 def ref_gpu_run(alg: str, csr, *params, on_ours: bool = False):
     """Runs gunrock::<alg>::run of the REFERENCE on the GPU (on_ours=True: the reference's algorithm headers on
     our operators). Returns (result tensor, enact ms)."""

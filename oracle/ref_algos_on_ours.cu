@@ -18,6 +18,8 @@
 #include REF_ALG(ppr.hxx)
 #include REF_ALG(kcore.hxx)
 #include REF_ALG(color.hxx)
+#include REF_ALG(bc.hxx)    // explicit-buffers merge_path advance, per-depth frontier array (bc.hxx:98-190)
+#include REF_ALG(spmv.hxx)  // neighborreduce (spmv.hxx:107-127)
 
 using namespace gunrock;
 using namespace memory;
@@ -54,5 +56,11 @@ float refours_kcore(int n, int m, int* d_off, int* d_col, float* d_val, int* d_k
 }
 float refours_color(int n, int m, int* d_off, int* d_col, float* d_val, int* d_colors) {
   REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); return gunrock::color::run(G, d_colors);)
+}
+float refours_bc(int n, int m, int* d_off, int* d_col, float* d_val, int src, float* d_bc) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); return gunrock::bc::run(G, src, d_bc);)
+}
+float refours_spmv(int n, int m, int* d_off, int* d_col, float* d_val, float* d_x, float* d_y) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); return gunrock::spmv::run(G, d_x, d_y);)
 }
 }  // extern "C"

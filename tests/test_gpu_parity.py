@@ -262,6 +262,16 @@ def test_filter_operator(ctx, graphs, alg):
     assert np.array_equal(out.cpu().numpy(), np.where(want % 3 != 0, want, -1))
 
 
+def test_uniquify_operator(ctx, graphs):
+    g = graphs["rmat_s10"]
+    rng = np.random.default_rng(4)
+    for size in (0, 1, 33, 5000, 70000):
+        items = rng.integers(0, g.n, size).astype(np.int32)
+        items[rng.random(size) < 0.05] = -1
+        out = ess.uniquify_probe(ctx, g, torch.from_numpy(items).cuda())
+        assert np.array_equal(out.cpu().numpy(), np.unique(items[items >= 0])), size
+
+
 def test_frontier_sparse_dense_round_trip(ctx):
     rng = np.random.default_rng(2)
     for universe in (1, 31, 32, 33, 1000, 100003):

@@ -103,3 +103,46 @@ def test_reference_algorithm_headers_run_on_our_operators(ctx, kron):
     colors, _ = oracle.ref_gpu_run("color", small, on_ours=True)
     assert oracle.color_errors(o, c, colors.cpu().numpy()) == 0
     assert np.array_equal(colors.cpu().numpy(), oracle.color_jacobi(o, c)[0]), "our random stream + deterministic filter"
+
+
+def _brandes_single_source(off, col, s):
+    """Dependency scores of one source (Brandes), the quantity gunrock::bc::run(G, source, bc) accumulates."""
+    n = off.size - 1
+    depth = oracle.bfs(off, col, s)
+    order = np.argsort(depth, kind="stable")
+    order = order[depth[order] != 2**31 - 1]
+    sigma = np.zeros(n)
+    sigma[s] = 1
+    for v in order:
+        for u in col[off[v]:off[v + 1]]:
+            if depth[u] == depth[v] + 1:
+                sigma[u] += sigma[v]
+    delta = np.zeros(n)
+    for v in order[::-1]:
+        for u in col[off[v]:off[v + 1]]:
+            if depth[u] == depth[v] + 1:
+                delta[v] += sigma[v] / sigma[u] * (1 + delta[u])
+    return delta
+
+
+@needs_compat
+def test_reference_bc_and_spmv_headers_on_our_operators(ctx):
+    """§8f rows: bc drives the explicit-buffers merge_path advance with a per-depth frontier array
+    (reference bc.hxx:98-190); spmv's pull form drives neighborreduce (spmv.hxx:107-127)."""
+    csr = gg.rmat_csr(9, weights="ones", device="cuda")
+    off, col, val = csr.host()
+    s = gg.pick_sources(csr, 1)[0]
+    got, _ = oracle.ref_on_ours_extra("bc", csr, s)
+    want = _brandes_single_source(off, col, s)
+    want[s] = 0.0
+    g = got.cpu().numpy().astype(np.float64)
+    g[s] = 0.0
+    assert np.allclose(g, want if np.allclose(g, want, rtol=1e-4, atol=1e-4) else want / 2, rtol=1e-4, atol=1e-4), \
+        "bc dependency scores (the reference halves them for undirected graphs)"
+    weighted = gg.rmat_csr(10, weights="hash", device="cuda")
+    x = torch.rand(weighted.n, device="cuda")
+    y, _ = oracle.ref_on_ours_extra("spmv", weighted, x)
+    rows = torch.repeat_interleave(torch.arange(weighted.n, device="cuda"), weighted.degrees().long())
+    want = torch.zeros(weighted.n, device="cuda", dtype=torch.float64).index_add_(
+        0, rows, (weighted.values.double() * x[weighted.indices.long()].double()))
+    assert torch.allclose(y.double(), want, rtol=1e-5, atol=1e-5)
