@@ -63,6 +63,7 @@ _SIGNATURES = {
     "ess_transpose_csr": (c_int, [c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ess_bfs": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int, c_int, c_float, c_float, POINTER(RunInfo)]),
     "ess_sssp": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int, POINTER(RunInfo)]),
+    "ess_sssp_near_far": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_float, POINTER(RunInfo)]),
     "ess_pagerank": (c_int, [c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_int, c_int, POINTER(RunInfo)]),
     "ess_ppr": (c_int, [c_void_p, c_void_p, c_int32, c_float, c_float, c_void_p, c_int, POINTER(RunInfo)]),
     "ess_kcore": (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(RunInfo)]),
@@ -238,6 +239,18 @@ def sssp(ctx: Context, g: Graph, source: int, lb: str = "block_mapped", out=None
     info = RunInfo()
     _check(lib().ess_sssp(ctx.handle, g.handle, int(source), _p(dist), LOAD_BALANCE[lb], byref(info)), "ess_sssp")
     return dist, info.as_dict()
+
+
+def sssp_near_far(ctx: Context, g: Graph, source: int, delta: float = 0.0, out=None):
+    """SSSP through operators::advance::execute_near_far (near/far ordering in one persistent kernel)."""
+    import torch
+    dist = _out(g.n, torch.float32, g.csr.indices) if out is None else out
+    info = RunInfo()
+    _check(lib().ess_sssp_near_far(ctx.handle, g.handle, int(source), _p(dist), float(delta), byref(info)),
+           "ess_sssp_near_far")
+    d = info.as_dict()
+    d.update(levels=int(info.reserved[0]), splits=int(info.reserved[1]), relaxations=int(info.reserved[2]))
+    return dist, d
 
 
 def pagerank(ctx: Context, g: Graph, alpha: float = 0.85, tol: float = 1e-6, max_iterations: int = 1000,

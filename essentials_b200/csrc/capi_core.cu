@@ -59,6 +59,10 @@ int ess_context_synchronize(ess_context_t ctx) {
 int ess_tune(const char* knob, int value) {
   ESS_TRY
   const std::string k = knob ? knob : "";
+  if (k == "near_far_ctas") {
+    gunrock::operators::advance::near_far_ctas_per_sm() = value < 1 ? 1 : value;
+    return 0;
+  }
   if (k == "pull_hints") {
     gunrock::operators::advance::kernels::pull_hints_enabled() = value;
     return 0;

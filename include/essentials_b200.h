@@ -112,6 +112,14 @@ ESS_API int ess_bfs(ess_context_t ctx, ess_graph_t g, int32_t source, int32_t* d
 /* gunrock::sssp::run — include/gunrock/algorithms/sssp.hxx:155-185. d_dist: n x float, FLT_MAX = unreachable. */
 ESS_API int ess_sssp(ess_context_t ctx, ess_graph_t g, int32_t source, float* d_dist, int lb, ess_run_info* info);
 
+/* Same distances as ess_sssp through operators::advance::execute_near_far (include/gunrock/framework/operators/
+ * advance/near_far.cuh): near/far priority ordering — the method the reference's load_balance_t::bucketing
+ * enumerator cites (configs.hxx:35) but leaves empty (advance/bucketing.hxx:31-36) — inside one persistent
+ * kernel. delta: bucket width (<= 0: mean edge weight). info->iterations = near levels; reserved[0] levels,
+ * [1] far-pile splits, [2] relaxations. */
+ESS_API int ess_sssp_near_far(ess_context_t ctx, ess_graph_t g, int32_t source, float* d_dist, float delta,
+                              ess_run_info* info);
+
 /* gunrock::pr::run — include/gunrock/algorithms/pr.hxx:183-216 (alpha 0.85, tol 1e-6 in examples/algorithms/pr/pr.cu:55-56).
  * pull != 0 gathers over the CSC view instead of scattering with atomics. */
 ESS_API int ess_pagerank(ess_context_t ctx, ess_graph_t g, float alpha, float tol, int max_iterations, float* d_p, int lb,

@@ -35,6 +35,16 @@ static __global__ void __launch_bounds__(256)
   mine = warp_max(mine);
   if (lane_id() == 0) atomicMax(result, __float_as_uint(mine));
 }
+/// *result += Σ x[i] in double (one atomic per warp).
+template <typename T>
+__global__ void __launch_bounds__(256) sum_kernel(const T* __restrict__ x, std::size_t n, double* result) {
+  double mine = 0;
+  for (std::size_t i = std::size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += std::size_t(gridDim.x) * blockDim.x)
+    mine += double(x[i]);
+  mine = warp_sum(mine);
+  if (lane_id() == 0) atomicAdd(result, mine);
+}
 /// *result &= all(flags) — counts zeros; result is the number of false entries.
 static __global__ void __launch_bounds__(256) count_false_kernel(const bool* __restrict__ flags, std::size_t n, counter_t* result) {
   counter_t mine = 0;

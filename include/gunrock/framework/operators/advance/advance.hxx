@@ -33,6 +33,7 @@
 #include <gunrock/framework/operators/configs.hxx>
 #include <gunrock/framework/operators/advance/kernels.cuh>
 #include <gunrock/framework/operators/advance/pull.cuh>
+#include <gunrock/framework/operators/advance/near_far.cuh>
 
 namespace gunrock {
 namespace operators {

@@ -9,7 +9,7 @@
 namespace gunrock {
 namespace thread {
 
-enum class cache_t { standard, read_only, streaming, volatile_ };
+enum class cache_t { standard, read_only, streaming, volatile_, global /* L2 only: coherent across SMs */ };
 
 template <cache_t modifier = cache_t::standard, typename type_t>
 __host__ __device__ __forceinline__ type_t load(type_t* ptr) {
@@ -20,6 +20,8 @@ __host__ __device__ __forceinline__ type_t load(type_t* ptr) {
     return __ldcs(ptr);
   else if constexpr (modifier == cache_t::volatile_)
     return *reinterpret_cast<volatile type_t*>(ptr);
+  else if constexpr (modifier == cache_t::global)
+    return __ldcg(ptr);
   else
     return *ptr;
 #else

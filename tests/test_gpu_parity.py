@@ -138,6 +138,33 @@ def test_sssp_rmat14_and_grid(ctx, lb):
     assert info["iterations"] >= 96 + 80 - 2
 
 
+@pytest.mark.parametrize("delta", [0.0, 1.0, 7.5, 64.0, 1e9])
+def test_sssp_near_far_bit_exact(ctx, graphs, golden, delta):
+    """operators::advance::execute_near_far (persistent near/far kernel) must give the reference distances for
+    every bucket width: delta -> inf degenerates to plain label correcting, tiny delta to Dijkstra order."""
+    for name in ("chesapeake", "rmat_s10", "grid_24x17"):
+        for s in golden[name]["sources"]:
+            dist, info = ess.sssp_near_far(ctx, graphs[name], int(s), delta=delta)
+            assert np.array_equal(dist.cpu().numpy(), golden[name][f"sssp_{s}"]), (name, int(s), delta)
+            assert info["levels"] >= 1
+
+
+def test_sssp_near_far_larger_graphs(ctx):
+    csr = gg.rmat_csr(14, weights="hash", device="cuda")  # hubs: exercises the warp-cooperative walk
+    off, col, val = csr.host()
+    g = ess.Graph(csr)
+    for s in gg.pick_sources(csr, 2):
+        dist, info = ess.sssp_near_far(ctx, g, s)
+        assert np.array_equal(dist.cpu().numpy(), oracle.sssp(off, col, val, s))
+    grid = gg.grid_csr(300, 200, device="cuda")
+    off, col, val = grid.host()
+    want = oracle.sssp(off, col, val, 17)
+    for delta in (0.0, 16.0, 200.0):
+        dist, info = ess.sssp_near_far(ctx, ess.Graph(grid), 17, delta=delta)
+        assert np.array_equal(dist.cpu().numpy(), want), delta
+        assert info["relaxations"] >= grid.m * 0 + 1
+
+
 # ------------------------------------------------------------------------------------------------ PageRank
 @pytest.mark.parametrize("mode", ["pull", "block_mapped", "merge_path", "bucketing", "thread_mapped"])
 def test_pagerank_directed_rmat(ctx, mode):
