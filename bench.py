@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--direction", default="optimized")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the SSSP-grid / PageRank / reference-GPU side runs")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall budget of the reference arm")
     return ap.parse_args()
 
@@ -57,6 +58,16 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_class):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json says which capture); None when there is none."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel_class, {}).get("bytes_per_launch")
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -262,8 +273,9 @@ def run_b200(args, rank, world, local_rank):
             prof = ctx.profile_read()
             ctx.profile(False)
         bytes_by_class = {
-            # bottom-up levels: 3 bitmaps streamed per level + row bounds of every walked vertex + in-edges read
-            "pull_step": acc["pull_steps"] * 3 * (n / 8) + acc["pull_vertices"] * 2 * sE + acc["pull_edges"] * 4,
+            # bottom-up levels: 3 bitmaps streamed per level + row bounds and head hint of every walked vertex +
+            # in-edges read from the adjacency lists
+            "pull_step": acc["pull_steps"] * 3 * (n / 8) + acc["pull_vertices"] * (2 * sE + 4) + acc["pull_edges"] * 4,
             # top-down levels: frontier id + row bounds per expanded vertex + column ids of its out-edges
             "push_expand": acc["push_vertices"] * (4 + 2 * sE) + acc["push_edges"] * 4,
         }
@@ -274,7 +286,7 @@ def run_b200(args, rank, world, local_rank):
         graph500_bytes = 8 * edges + (2 * sE + 12) * verts
         out["roofline"] = {
             "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-            "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak_gbs, "traffic": ncu_traffic(dom), "peak_source": peak_src,
             "launches": d_launches, "avg_launch_ms": d_ms / max(d_launches, 1),
             "algorithmic_bytes_per_launch": bytes_by_class[dom] / max(d_launches, 1),
             "kernel_ms_per_step": {k: v / K for k, v in kernel_ms.items() if v},
@@ -326,6 +338,12 @@ def run_b200(args, rank, world, local_rank):
                 "depths_equal_gpu": same}
             if not same:
                 out["parity_error"] = "GPU depths differ from the CPU reference"
+        # ---- side measurements (BASELINE configs 3 and 4, and the reference's own GPU path); never fatal ----
+        if not args.no_extras and rank == 0:
+            try:
+                out["other_configs"] = side_runs(args, ctx, csr, graph, timed, work, dev)
+            except Exception as e:  # the headline line must survive anything here
+                out["other_configs"] = {"error": repr(e)[:300]}
     else:
         # ---- multi-GPU: NVLink-side accounting + e2e with this rank's partition in host memory ---------
         out["config"]["exchange"] = ("per level: all_to_all of candidate bitmap slices (top-down levels only) + one "
@@ -366,6 +384,58 @@ def run_b200(args, rank, world, local_rank):
 
     if rank == 0:
         print(json.dumps(out), flush=True)
+
+
+def side_runs(args, ctx, csr, graph, timed, work, dev):
+    """BASELINE configs 3/4 and the reference GPU implementation on this same device (one run each)."""
+    import torch
+
+    import essentials_b200 as ess
+    import oracle
+    from essentials_b200 import graphgen as gg
+    res = {}
+    # the reference's own GPU BFS (block_mapped + Thrust, built for sm_100) on the bench graph, same source
+    if oracle.have_ref_gpu() and csr.offsets.dtype == torch.int32:
+        s = timed[0]
+        for _ in range(2):
+            ref_depth, ref_ms = oracle.ref_gpu_run("bfs", csr, s)
+        ours, info = ess.bfs(ctx, graph, s, lb=args.lb, direction=args.direction)
+        res["reference_gpu_bfs"] = {"workload": f"same graph, source {s}", "reference_enact_ms": ref_ms,
+                                    "reference_gteps": work[s][1] / ref_ms / 1e6, "ours_enact_ms": info["enact_ms"],
+                                    "ours_gteps": work[s][1] / info["enact_ms"] / 1e6,
+                                    "depths_equal": bool(torch.equal(ours, ref_depth))}
+        del ref_depth
+    # config 3: SSSP on the 4900 x 4900 grid
+    grid = gg.grid_csr(4900, 4900, device=dev)
+    gg_graph = ess.Graph(grid)
+    d_nf, i_nf = ess.sssp_near_far(ctx, gg_graph, 0)
+    d_lc, i_lc = ess.sssp(ctx, gg_graph, 0, lb="block_mapped")
+    res["sssp_grid_4900"] = {"n": grid.n, "m": grid.m, "near_far_enact_ms": i_nf["enact_ms"],
+                             "near_far_gteps": grid.m / i_nf["enact_ms"] / 1e6, "near_far_levels": i_nf["levels"],
+                             "relaxations_per_edge": i_nf["relaxations"] / grid.m,
+                             "label_correcting_block_mapped_enact_ms": i_lc["enact_ms"],
+                             "distances_equal": bool(torch.equal(d_nf, d_lc))}
+    if oracle.have_ref_gpu():
+        ref_dist, ref_ms = oracle.ref_gpu_run("sssp", grid, 0)
+        res["sssp_grid_4900"].update(reference_gpu_enact_ms=ref_ms, equal_reference_gpu=bool(torch.equal(d_nf, ref_dist)))
+    del gg_graph, grid, d_nf, d_lc
+    # config 4: PageRank on directed RMAT scale-25
+    pr_csr = gg.rmat_csr(25, args.edge_factor, symmetric=False, weights="ones", device=dev)
+    pr_graph = ess.Graph(pr_csr, csc=ess.transpose(pr_csr))
+    p_pull, i_pull = ess.pagerank(ctx, pr_graph, pull=True)
+    p_push, i_push = ess.pagerank(ctx, pr_graph, lb="merge_path")
+    rel = ((p_pull.double() - p_push.double()).abs().sum() / p_pull.double().sum()).item()
+    res["pagerank_rmat25"] = {"n": pr_csr.n, "m": pr_csr.m, "iterations": i_pull["iterations"],
+                              "pull_ms_per_iteration": i_pull["enact_ms"] / max(i_pull["iterations"], 1),
+                              "push_merge_path_ms_per_iteration": i_push["enact_ms"] / max(i_push["iterations"], 1),
+                              "pull_gteps": pr_csr.m * i_pull["iterations"] / i_pull["enact_ms"] / 1e6,
+                              "rel_l1_push_vs_pull": rel}
+    if oracle.have_ref_gpu():
+        ref_p, ref_ms = oracle.ref_gpu_run("pr", pr_csr, 0.85, 1e-6)
+        res["pagerank_rmat25"].update(reference_gpu_enact_ms=ref_ms, ours_pull_enact_ms=i_pull["enact_ms"],
+                                      rel_l1_vs_reference_gpu=((p_pull.double() - ref_p.double()).abs().sum()
+                                                               / ref_p.double().sum()).item())
+    return res
 
 
 def main():
