@@ -19,6 +19,7 @@
 #include <type_traits>
 #include <utility>
 #include <gunrock/b200/warp.cuh>
+#include <gunrock/framework/operators/advance/directional.cuh>
 #include <gunrock/cuda/context.hxx>
 #include <gunrock/graph/graph.hxx>
 
@@ -64,37 +65,6 @@ __global__ void __launch_bounds__(256)
   __syncwarp();
   mine = b200::warp_sum(mine);
   if (b200::lane_id() == 0 && mine) atomicAdd(counters + scratch_t::aux2, mine);
-}
-
-/**
- * @brief Operator pair for direction-optimised advance. `push` is the ordinary advance operator (several
- * threads may race on the same neighbour, so it needs atomics); `pull` is what a bottom-up level calls: the
- * destination vertex is owned by exactly one thread and is known to be outside the visited set, so the
- * same update can usually be a plain store (BFS: `depth[v] = level; return true`) and the thread does not
- * wait for an atomic's round trip. Built with advance::directional(push, pull); a plain lambda is used for
- * both directions.
- */
-template <typename push_t, typename pull_t>
-struct directional_operator_t {
-  push_t push;
-  pull_t pull;
-  template <typename V, typename E, typename W>
-  __host__ __device__ __forceinline__ bool operator()(V& src, V& dst, E& edge, W& weight) const {
-    return push(src, dst, edge, weight);
-  }
-};
-
-template <typename T, typename = void>
-struct has_pull_operator : std::false_type {};
-template <typename T>
-struct has_pull_operator<T, std::void_t<decltype(std::declval<T>().pull)>> : std::true_type {};
-
-template <typename operator_t, typename vertex_t, typename edge_t, typename weight_t>
-__device__ __forceinline__ bool call_pull(operator_t& op, vertex_t src, vertex_t dst, edge_t edge, weight_t weight) {
-  if constexpr (has_pull_operator<operator_t>::value)
-    return op.pull(src, dst, edge, weight);
-  else
-    return op(src, dst, edge, weight);
 }
 
 /**
