@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=int, default=0,
-                    help="Kronecker scale; default 24 (BASELINE config 2) at every GPU count = strong scaling")
+                    help="Kronecker scale; default 24 + log2(gpus): BASELINE config 2 on one GPU and the same "
+                         "number of edges PER GPU on more (weak scaling of the 1-D partitioned BFS); an explicit "
+                         "--scale fixes the total work (strong scaling)")
     ap.add_argument("--edge-factor", type=int, default=16)
     ap.add_argument("--lb", default="merge_path")
     ap.add_argument("--direction", default="optimized")
@@ -157,7 +159,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "BFS GTEPS", "value": val, "unit": "GTEPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": f"BFS kron scale-{args.scale} ef-{args.edge_factor} (sample: scale-{scale})",
                    "n": csr.n, "m": csr.m},
         "cpu_baseline": {"value": val, "unit": "GTEPS", "cores": 1, "kind": kind, "sample": sample},
@@ -248,7 +250,7 @@ def run_b200(args, rank, world, local_rank):
 
     out = {
         "metric": "BFS GTEPS", "value": value, "unit": "GTEPS", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": f"BFS kron scale-{args.scale} ef-{args.edge_factor} symmetrised, {K} random sources",
                    "n": n, "m": m, "edge_t_bits": offset_bits, "advance": f"{args.lb}/{args.direction}",
@@ -440,8 +442,10 @@ def side_runs(args, ctx, csr, graph, timed, work, dev):
 
 def main():
     args = parse()
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    args.scaling = "strong" if args.scale > 0 and world_env > 1 else "weak"
     if args.scale <= 0:
-        args.scale = 24
+        args.scale = 24 + max(world_env.bit_length() - 1, 0)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -79,6 +79,7 @@ _SIGNATURES = {
     "ess_bits_to_list_async": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "ess_bfs_partition_step": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int64]),
+    "ess_bfs_merge_gathered": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "ess_bfs_absorb": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int64, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
 }

@@ -128,6 +128,27 @@ __global__ void __launch_bounds__(256)
   if (b200::lane_id() == 0 && edges) atomicAdd(counts + 1, edges);
 }
 
+/// After the per-level all_gather: unpack the P rows of (next-frontier slice | 2 x int64 counters) into the
+/// replicated frontier bitmap, fold it into the visited bitmap and collect the counters in one small array.
+static __global__ void __launch_bounds__(256)
+    merge_gathered_kernel(const unsigned* __restrict__ gathered, int world, unsigned slice_words,
+                          unsigned* __restrict__ frontier_bits, unsigned* __restrict__ visited_bits,
+                          long long* __restrict__ counts_out) {
+  const unsigned row = slice_words + 4;
+  const std::size_t total = std::size_t(world) * slice_words;
+  for (std::size_t w = std::size_t(blockIdx.x) * blockDim.x + threadIdx.x; w < total;
+       w += std::size_t(gridDim.x) * blockDim.x) {
+    const unsigned r = unsigned(w / slice_words), k = unsigned(w % slice_words);
+    const unsigned bits = gathered[std::size_t(r) * row + k];
+    frontier_bits[w] = bits;
+    if (bits) visited_bits[w] |= bits;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 2 * world) {
+    const int r = threadIdx.x / 2, c = threadIdx.x % 2;
+    counts_out[threadIdx.x] = reinterpret_cast<const long long*>(gathered + std::size_t(r) * row + slice_words)[c];
+  }
+}
+
 inline int fail_pull_via_step() {
   return ess::fail("ess_bfs_partition_step: bottom-up levels go through ess_bfs_partition_pull");
 }
@@ -291,6 +312,21 @@ int ess_bfs_partition_pull(ess_context_t ctx, ess_graph_t g, int64_t row_begin, 
     return partition_pull(ctx, G, row_begin, level, d_frontier_bits, d_visited_bits, d_next_slice, d_depth_local,
                           d_counts);
   })
+  ESS_CATCH
+}
+
+int ess_bfs_merge_gathered(ess_context_t ctx, const uint32_t* d_gathered, int32_t world, int64_t slice_words,
+                           uint32_t* d_frontier_bits, uint32_t* d_visited_bits, int64_t* d_counts_out) {
+  ESS_TRY
+  if (!ctx || !d_gathered || !d_counts_out) return ess::fail("ess_bfs_merge_gathered: null argument");
+  if (world < 1 || world > 128) return ess::fail("ess_bfs_merge_gathered: world size out of range");
+  auto* c = ctx->single();
+  const std::size_t total = std::size_t(world) * std::size_t(slice_words);
+  merge_gathered_kernel<<<gcuda::persistent_grid(*c, (total + 255) / 256, 8), 256, 0, c->stream()>>>(
+      d_gathered, world, unsigned(slice_words), d_frontier_bits, d_visited_bits,
+      reinterpret_cast<long long*>(d_counts_out));
+  error::check_last("merge gathered");
+  return 0;
   ESS_CATCH
 }
 

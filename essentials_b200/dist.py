@@ -65,6 +65,12 @@ class CudaBackend:
         ess._check(ess.lib().ess_bits_to_list_async(self.ctx.handle, ess._p(next_slice), int(next_slice.numel()) * 32,
                                                     ess._p(fresh_list)), "ess_bits_to_list_async")
 
+    def merge(self, gathered, world: int, slice_words: int, frontier_bits, visited_bits, counts_out):
+        ess = self.ess
+        ess._check(ess.lib().ess_bfs_merge_gathered(self.ctx.handle, ess._p(gathered), world, slice_words,
+                                                    ess._p(frontier_bits), ess._p(visited_bits), ess._p(counts_out)),
+                   "ess_bfs_merge_gathered")
+
     def absorb(self, level: int, candidates, n_slices: int, stride_words: int, visited_bits, next_slice, depth_local,
                fresh_list, counts):
         ess = self.ess
@@ -102,6 +108,10 @@ class PartitionedBFS:
         self.send = torch.zeros(self.wper + 4, **i32)
         self.recv = torch.zeros(world * (self.wper + 4), **i32)
         self.a2a_recv = torch.zeros(self.words, **i32)
+        self.counts_dev = torch.zeros(2 * world, dtype=torch.int64, device=device)
+        self.counts_host = torch.zeros(2 * world, dtype=torch.int64)
+        if device.type == "cuda":
+            self.counts_host = self.counts_host.pin_memory()
         self.deg_local = (csr_local.offsets[1:] - csr_local.offsets[:-1]).to(torch.int64)
         m = torch.tensor([int(csr_local.indices.numel())], dtype=torch.int64, device=device)
         dist.all_reduce(m)
@@ -116,6 +126,10 @@ class PartitionedBFS:
         self.bytes_exchanged = 0
 
     # ------------------------------------------------------------------------------------------------
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+
     def owner(self, v: int) -> int:
         return v // self.per
 
@@ -189,10 +203,12 @@ class PartitionedBFS:
             dist.all_gather_into_tensor(self.recv, self.send)
             t0 = mark("all_gather", t0)
             exchanged += (self.world - 1) * (self.wper + 4) * 4
-            rows = self.recv.view(self.world, self.wper + 4)
-            self.frontier_bits.view(self.world, self.wper).copy_(rows[:, : self.wper])
-            self.visited_bits[: self.words].bitwise_or_(self.frontier_bits)
-            per_rank = rows[:, self.wper:].contiguous().view(torch.int64).cpu()  # the one host sync of the level
+            # one kernel unpacks the gathered rows into the frontier bitmap, folds it into visited and collects the
+            # counters; reading them is the one host sync of the level
+            self.backend.merge(self.recv, self.world, self.wper, self.frontier_bits, self.visited_bits, self.counts_dev)
+            self.counts_host.copy_(self.counts_dev, non_blocking=True)
+            self._sync()
+            per_rank = self.counts_host.view(self.world, 2)
             my_count = int(per_rank[self.rank, 0])
             prev_n_f, n_f, m_f = n_f, int(per_rank[:, 0].sum()), int(per_rank[:, 1].sum())
             m_u -= m_f

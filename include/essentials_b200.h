@@ -197,6 +197,11 @@ ESS_API int ess_bfs_partition_step(ess_context_t ctx, ess_graph_t g, int64_t row
 ESS_API int ess_bfs_partition_pull(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int32_t level,
                                    const uint32_t* d_frontier_bits, uint32_t* d_visited_bits,
                                    uint32_t* d_next_slice, int32_t* d_depth_local, int64_t* d_counts);
+/* After the all_gather of a level: d_gathered holds `world` rows of (slice_words next-frontier words | 2 x int64
+ * counters). Unpacks them into the replicated frontier bitmap, ORs it into the visited bitmap and copies the
+ * counters to d_counts_out (2*world int64). Enqueue only. */
+ESS_API int ess_bfs_merge_gathered(ess_context_t ctx, const uint32_t* d_gathered, int32_t world, int64_t slice_words,
+                                   uint32_t* d_frontier_bits, uint32_t* d_visited_bits, int64_t* d_counts_out);
 ESS_API int ess_bfs_absorb(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int32_t level,
                            const uint32_t* d_candidates, int32_t n_slices, int64_t slice_stride_words,
                            uint32_t* d_visited_bits, uint32_t* d_next_slice, int32_t* d_depth_local,

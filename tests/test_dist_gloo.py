@@ -47,6 +47,12 @@ class NumpyBackend:
         counts.view(torch.int64)[0] += int(found.sum())
         counts.view(torch.int64)[1] += int(deg[found].sum())
 
+    def merge(self, gathered, world, slice_words, frontier_bits, visited_bits, counts_out):
+        rows = gathered.view(world, slice_words + 4)
+        frontier_bits.view(world, slice_words).copy_(rows[:, :slice_words])
+        visited_bits[: world * slice_words].bitwise_or_(frontier_bits)
+        counts_out.copy_(rows[:, slice_words:].contiguous().view(torch.int64).reshape(-1))
+
     def gather_fresh(self, next_slice, fresh_list):
         ids = np.nonzero(self._bits(next_slice, self.n_local))[0]
         fresh_list[: ids.size] = torch.from_numpy(ids.astype(np.int32))
