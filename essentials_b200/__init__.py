@@ -82,6 +82,12 @@ _SIGNATURES = {
     "ess_bfs_merge_gathered": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "ess_bfs_absorb": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int64, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
+    "ess_nccl_unique_id": (c_int, [c_void_p]),
+    "ess_dist_create": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, POINTER(c_void_p)]),
+    "ess_dist_destroy": (c_int, [c_void_p]),
+    "ess_dist_bfs": (c_int, [c_void_p, c_int64, c_float, c_float, POINTER(RunInfo)]),
+    "ess_dist_copy_depth": (c_int, [c_void_p, c_void_p]),
+    "ess_dist_depth_local": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64)]),
 }
 
 _lib = None

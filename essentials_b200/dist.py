@@ -249,6 +249,76 @@ class PartitionedBFS:
         return out
 
 
+class NativePartitionedBFS:
+    """The same partitioned BFS with the whole level loop in C++ and NCCL called directly (ess_dist_bfs):
+    no Python or torch dispatch on the per-level critical path. Mirrors PartitionedBFS's interface."""
+
+    def __init__(self, csr_local, row_begin: int, n_global: int, rank: int, world: int, device, stream=None):
+        import essentials_b200 as ess
+        self.ess, self.rank, self.world, self.device = ess, rank, world, device
+        self.n_global, self.per, self.row_begin = n_global, n_global // world, row_begin
+        self.csr = csr_local
+        self.offset_bits = 64 if csr_local.offsets.element_size() == 8 else 32
+        self.backend = CudaBackend(csr_local, row_begin, n_global, device,
+                                   stream if stream is not None else torch.cuda.current_stream(device))
+        self.deg_local = (csr_local.offsets[1:] - csr_local.offsets[:-1]).to(torch.int64)
+        m = torch.tensor([int(csr_local.indices.numel())], dtype=torch.int64, device=device)
+        dist.all_reduce(m)
+        self.m_global = int(m.item())
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            ess._check(ess.lib().ess_nccl_unique_id(buf), "ess_nccl_unique_id")
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.to(device)
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().tolist())
+        h = ctypes.c_void_p()
+        ess._check(ess.lib().ess_dist_create(self.backend.ctx.handle, self.backend.graph.handle, rank, world, n_global,
+                                             raw, byref(h)), "ess_dist_create")
+        self.handle = h
+        ptr, cnt = ctypes.c_void_p(), c_int64(0)
+        ess._check(ess.lib().ess_dist_depth_local(h, byref(ptr), byref(cnt)), "ess_dist_depth_local")
+        self._depth_ptr, self._depth_count = ptr.value, cnt.value
+        self.depth_local = torch.empty(self.per, dtype=torch.int32, device=device)
+        self.levels = self.pull_levels = 0
+        self.bytes_exchanged = 0
+
+    def bfs(self, source: int, trace=None) -> dict:
+        ess = self.ess
+        info = ess.RunInfo()
+        ess._check(ess.lib().ess_dist_bfs(self.handle, int(source), 0.0, 0.0, byref(info)), "ess_dist_bfs")
+        self.levels, self.pull_levels = int(info.iterations), int(info.pull_steps)
+        self.bytes_exchanged = int(info.reserved[0])
+        return {"iterations": self.levels, "pull_steps": self.pull_levels, "push_steps": int(info.push_steps),
+                "nvlink_bytes_received": self.bytes_exchanged, "enact_ms": float(info.enact_ms)}
+
+    def _fetch_depth(self):
+        """Copy the library-owned depth slice into self.depth_local (device to device, on the context's stream)."""
+        self.ess._check(self.ess.lib().ess_dist_copy_depth(self.handle, self.ess._p(self.depth_local)),
+                        "ess_dist_copy_depth")
+
+    def reached_work(self):
+        self._fetch_depth()
+        r = self.depth_local != INF
+        t = torch.stack([r.sum().to(torch.int64), self.deg_local[r].sum()])
+        dist.all_reduce(t)
+        return int(t[0]), int(t[1])
+
+    def gather_depth(self) -> torch.Tensor:
+        self._fetch_depth()
+        full = torch.empty(self.n_global, dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(full, self.depth_local)
+        return full
+
+    pick_sources = PartitionedBFS.pick_sources
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ess.lib().ess_dist_destroy(self.handle)
+            self.handle = None
+
+
 def _bit(b: int) -> int:
     """int32 value with only bit b set (bit 31 is the sign bit)."""
     return -(1 << 31) if b == 31 else (1 << b)
@@ -263,15 +333,19 @@ def _pack_bits(flags: torch.Tensor) -> torch.Tensor:
     return word.to(torch.int32)
 
 
-def build_partitioned(scale: int, edge_factor: int, rank: int, world: int, device, stream=None, seed: int = 1):
+def build_partitioned(scale: int, edge_factor: int, rank: int, world: int, device, stream=None, seed: int = 1,
+                      native: bool = True):
     """Product constructor: regenerate the counter-based Kronecker edge list, keep this rank's rows, bind the
-    CUDA backend."""
+    CUDA backend. native=True drives the level loop from C++ with NCCL (ess_dist_bfs); False keeps the
+    torch.distributed loop of PartitionedBFS."""
     from . import graphgen as gg
     n = 1 << scale
     per = n // world
     ctxmgr = torch.cuda.stream(stream) if stream is not None else _null()
     with ctxmgr:
         csr = gg.rmat_csr(scale, edge_factor, seed=seed, device=device, row_range=(rank * per, (rank + 1) * per))
+        if native:
+            return NativePartitionedBFS(csr, rank * per, n, rank, world, device, stream)
         backend = CudaBackend(csr, rank * per, n, device, stream if stream is not None else torch.cuda.current_stream())
         return PartitionedBFS(csr, rank * per, n, rank, world, backend, device)
 

@@ -207,6 +207,21 @@ ESS_API int ess_bfs_absorb(ess_context_t ctx, ess_graph_t g, int64_t row_begin, 
                            uint32_t* d_visited_bits, uint32_t* d_next_slice, int32_t* d_depth_local,
                            int32_t* d_fresh_list, int64_t* d_counts);
 
+/* ---- native multi-GPU BFS driver: the level loop above in C++ with NCCL called directly ----------------
+ * One process per GPU. `unique_id`: 128 bytes from ess_nccl_unique_id on rank 0, distributed by the host
+ * (e.g. torch.distributed broadcast). `g`: this rank's partition (symmetric = 2, hints built). NCCL is
+ * resolved at run time from the libnccl already loaded in the process. ess_dist_bfs runs one whole BFS from
+ * the GLOBAL vertex id `source`: info->enact_ms is the device time of the run, iterations/pull_steps the
+ * levels, reserved[0] the bytes received per rank. Depths of the owned rows: ess_dist_depth_local. */
+typedef struct ess_dist_s* ess_dist_t;
+ESS_API int ess_nccl_unique_id(void* out_128_bytes);
+ESS_API int ess_dist_create(ess_context_t ctx, ess_graph_t g, int rank, int world, int64_t n_global,
+                            const void* unique_id, ess_dist_t* out);
+ESS_API int ess_dist_destroy(ess_dist_t d);
+ESS_API int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_info* info);
+ESS_API int ess_dist_depth_local(ess_dist_t d, int32_t** d_depth_local, int64_t* count);
+ESS_API int ess_dist_copy_depth(ess_dist_t d, int32_t* d_out); /* owned depth slice -> caller buffer, on the stream */
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,12 +19,13 @@ from essentials_b200 import graphgen as gg  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=int, default=20)
 ap.add_argument("--sources", type=int, default=4)
+ap.add_argument("--python-loop", action="store_true", help="use the torch.distributed level loop instead of ess_dist_bfs")
 args = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-runner = edist.build_partitioned(args.scale, 16, rank, world, dev)
+runner = edist.build_partitioned(args.scale, 16, rank, world, dev, native=not args.python_loop)
 srcs = runner.pick_sources(args.sources)
 ok = True
 if rank == 0:
@@ -42,10 +43,11 @@ for s in [0] + srcs:
         want, _ = ess.bfs(ctx, g, s, lb="merge_path", direction="optimized")
         same = bool(torch.equal(want, depth))
         ok &= same
-        print(f"src={s} levels={info['iterations']} pull={info['pull_steps']} wall={ms:.2f} ms equal={same}", flush=True)
+        print(f"src={s} levels={info['iterations']} pull={info['pull_steps']} wall={ms:.2f} ms "
+              f"device={info['enact_ms']:.2f} ms equal={same}", flush=True)
 trace = []
 runner.bfs(srcs[-1], trace=trace)
-if rank == 0:
+if rank == 0 and trace:
     import collections
     agg = collections.OrderedDict()
     for lvl, phase, dt in trace:
