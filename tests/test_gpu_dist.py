@@ -11,8 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (CPU gloo test covers the host logic)")
-def test_partitioned_bfs_two_gpus():
+@pytest.mark.parametrize("loop", ["native", "python"])
+def test_partitioned_bfs_two_gpus(loop):
+    """Both drivers of the 1-D partitioned BFS — ess_dist_bfs (C++ + NCCL) and the torch.distributed loop that the
+    gloo tests cover — must reproduce the single-GPU depths."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "scripts", "dist_check.py"), "--scale", "18"]
+           "127.0.0.1", "--master-port", "29517" if loop == "native" else "29518",
+           os.path.join(ROOT, "scripts", "dist_check.py"), "--scale", "18"] + (["--python-loop"] if loop == "python" else [])
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DIST_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
