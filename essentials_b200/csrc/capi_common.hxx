@@ -45,6 +45,7 @@ struct ess_graph_s {
   gunrock::memory::device_array_t<int32_t> hint_head;
   gunrock::memory::device_array_t<int32_t> hint_edge32;
   gunrock::memory::device_array_t<int64_t> hint_edge64;
+  gunrock::memory::device_array_t<unsigned> hint_isolated;
 };
 
 #define ESS_TRY try {

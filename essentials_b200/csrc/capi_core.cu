@@ -144,12 +144,15 @@ int ess_graph_build_pull_hints(ess_graph_t h, const int32_t* d_degree_of_id) {
   if (!h || !h->has_csc) return ess::fail("ess_graph_build_pull_hints: graph has no CSC view");
   if (h->n <= 0 || h->m <= 0) return 0;
   h->hint_head.resize(std::size_t(h->n));
+  h->hint_isolated.resize((std::size_t(h->n) + 31) / 32 + 1);
   if (h->offset_bits == 64) {
     h->hint_edge64.resize(std::size_t(h->n));
-    graph::build::pull_hints(h->g64, h->hint_head.data(), h->hint_edge64.data(), 0, d_degree_of_id);
+    graph::build::pull_hints(h->g64, h->hint_head.data(), h->hint_edge64.data(), 0, d_degree_of_id,
+                             h->hint_isolated.data());
   } else {
     h->hint_edge32.resize(std::size_t(h->n));
-    graph::build::pull_hints(h->g32, h->hint_head.data(), h->hint_edge32.data(), 0, d_degree_of_id);
+    graph::build::pull_hints(h->g32, h->hint_head.data(), h->hint_edge32.data(), 0, d_degree_of_id,
+                             h->hint_isolated.data());
   }
   return 0;
   ESS_CATCH

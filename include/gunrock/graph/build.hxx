@@ -140,6 +140,21 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+/// Bitmap of vertices with an empty list (padding bits of the last word set too): 1 warp per 32-vertex word.
+template <typename vertex_t, typename edge_t>
+__global__ void __launch_bounds__(256)
+    isolated_bitmap_kernel(vertex_t n, const edge_t* __restrict__ offsets, unsigned* __restrict__ words) {
+  const unsigned lane = threadIdx.x & 31;
+  const std::size_t n_words = (std::size_t(n) + 31) / 32;
+  const std::size_t warps = (std::size_t(gridDim.x) * blockDim.x) >> 5;
+  for (std::size_t w = (std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
+    const std::size_t v = w * 32 + lane;
+    const bool skip = v >= std::size_t(n) || offsets[v + 1] == offsets[v];
+    const unsigned word = __ballot_sync(0xffffffffu, skip);
+    if (lane == 0) words[w] = word;
+  }
+}
+
 template <typename vertex_t, typename edge_t, typename weight_t>
 void transpose_on_device(vertex_t n, edge_t m, const edge_t* Ap, const vertex_t* J, const weight_t* X,
                          vertex_t* I, edge_t* Aj, weight_t* csc_values) {
@@ -208,7 +223,10 @@ auto from_csr(vertex_t const& r, vertex_t const& c, edge_t const& nnz, edge_t* A
  */
 template <typename graph_type>
 void pull_hints(graph_type& G, typename graph_type::vertex_type* head, typename graph_type::edge_type* head_edge,
-                cudaStream_t stream = 0, const typename graph_type::vertex_type* degree_of = nullptr) {
+                cudaStream_t stream = 0, const typename graph_type::vertex_type* degree_of = nullptr,
+                unsigned* isolated_words = nullptr) {
+  // isolated_words (optional, ceil(n/32) words): receives the bitmap of vertices without in-edges, the start
+  // state of the visited set of every direction-optimised traversal (saves an n-length pass per run).
   // degree_of (optional): degree of every vertex id that can appear as an in-neighbour. Needed when G holds
   // only a row range of a partitioned graph, whose offsets cannot answer degree queries for remote ids.
   using csr_v = typename graph_type::graph_csr_view_t;
@@ -224,8 +242,10 @@ void pull_hints(graph_type& G, typename graph_type::vertex_type* head, typename 
   if (n > 0)
     detail::pull_hints_kernel<<<2048, 256, 0, stream>>>(n, c.get_column_offsets(), c.get_row_indices(), degree_offsets,
                                                         degree_of, head, head_edge);
+  if (n > 0 && isolated_words)
+    detail::isolated_bitmap_kernel<<<2048, 256, 0, stream>>>(n, c.get_column_offsets(), isolated_words);
   error::throw_if_exception(cudaStreamSynchronize(stream), "pull_hints");
-  c.set_pull_hints(head, head_edge);
+  c.set_pull_hints(head, head_edge, isolated_words);
 }
 
 /// Wrap pre-built CSR and CSC arrays (no computation): used by the C ABI when the caller owns both.

@@ -203,10 +203,13 @@ class graph_csc_t {
   __host__ __device__ __forceinline__ auto get_column_offsets() const { return s.offsets; }
   __host__ __device__ __forceinline__ auto get_row_indices() const { return s.indices; }
   /// Bottom-up hints (B200 addition): caller-owned arrays filled by graph::build::pull_hints.
-  __host__ __device__ void set_pull_hints(const vertex_t* head, const edge_t* head_edge) {
+  __host__ __device__ void set_pull_hints(const vertex_t* head, const edge_t* head_edge,
+                                          const unsigned* isolated = nullptr) {
     hint_head = head;
     hint_edge = head_edge;
+    hint_isolated = isolated;
   }
+  __host__ __device__ __forceinline__ const unsigned* get_pull_hint_isolated() const { return hint_isolated; }
   __host__ __device__ __forceinline__ const vertex_t* get_pull_hint_heads() const { return hint_head; }
   __host__ __device__ __forceinline__ const edge_t* get_pull_hint_edges() const { return hint_edge; }
   __host__ __device__ __forceinline__ auto get_nonzero_values() const { return s.values; }
@@ -230,6 +233,7 @@ class graph_csc_t {
   store_t s;
   const vertex_t* hint_head = nullptr;
   const edge_t* hint_edge = nullptr;
+  const unsigned* hint_isolated = nullptr;
 };
 
 template <typename vertex_t, typename edge_t, typename weight_t>
@@ -410,6 +414,7 @@ struct adjacency_t {
   // largest degree and the id of that in-edge; null when the graph was built without them.
   const vertex_t* head = nullptr;
   const edge_t* head_edge = nullptr;
+  const unsigned* isolated = nullptr;  ///< bitmap of vertices without in-edges (padding bits set), or null
 };
 
 /// The arrays an advance walks: CSR (rows -> out-neighbours) for forward, CSC (columns -> in-neighbours)
@@ -426,7 +431,7 @@ auto adjacency_of(const graph_type& G) {
     const csc_v& c = G;
     return adjacency_t<V, E, W>{c.get_column_offsets(), c.get_row_indices(),     c.get_nonzero_values(),
                                 c.get_number_of_vertices(), c.get_number_of_edges(), c.get_pull_hint_heads(),
-                                c.get_pull_hint_edges()};
+                                c.get_pull_hint_edges(),    c.get_pull_hint_isolated()};
   } else {
     using csr_v = typename graph_type::graph_csr_view_t;
     static_assert(graph_type::template contains_representation<csr_v>(),
