@@ -230,6 +230,90 @@ int partition_step(ess_context_t ctx, graph_t& G, int64_t row_begin, int64_t n_g
   return 0;
 }
 
+
+// ---- 1-D partitioned SSSP ------------------------------------------------------------------------
+// Every rank keeps a full-length `replica` of tentative distances. Owned entries are exact after each exchange;
+// the others are only this rank's best candidates so far (a pruning bound: a candidate that does not beat it
+// was already sent). A relaxation round = relax (atomic min into the replica) -> reduce_scatter(min) so each
+// owner receives the best candidate for its rows -> collect (owned rows whose distance dropped form the next
+// active list).
+
+/// Relax the out-edges of this rank's active rows (LOCAL row ids): replica[nbr] = min(replica[nbr], dist[src] + w).
+template <typename graph_t>
+int partition_relax(ess_context_t ctx, graph_t& G, const int32_t* d_active_list, int64_t active_count,
+                    const float* d_dist_local, float* d_replica) {
+  using edge_t = typename graph_t::edge_type;
+  if (active_count <= 0) return 0;
+  auto* c = ctx->single();
+  borrowed_frontier_t<edge_t> in, out;
+  in.ptr = const_cast<int32_t*>(d_active_list);
+  in.count = in.cap = std::size_t(active_count);
+  static thread_local memory::device_array_t<edge_t> segments;
+  const float* dist_local = d_dist_local;
+  float* replica = d_replica;
+  auto op = [dist_local, replica] __device__(int32_t const& src, int32_t const& nbr, edge_t const& e,
+                                             float const& w) -> bool {
+    const float nd = dist_local[src] + w;
+    if (nd < replica[nbr]) math::atomic::min(replica + nbr, nd);  // the plain read only prunes
+    return false;
+  };
+  using namespace operators;
+  auto& scratch = c->scratch();
+  const bool was_async = scratch.async_when_no_output;
+  scratch.async_when_no_output = true;
+  advance::execute<load_balance_t::merge_path, advance_direction_t::forward, advance_io_type_t::vertices,
+                   advance_io_type_t::none>(G, op, &in, &out, segments, *ctx->ctx);
+  scratch.async_when_no_output = was_async;
+  return 0;
+}
+
+/// Owner side after the exchange: rows whose reduced candidate beats the stored distance adopt it and join the
+/// next active list; counts[0] += rows, counts[1] += their out-degrees. 4 rows per thread, one atomic per CTA.
+template <typename edge_t>
+static __global__ void __launch_bounds__(256)
+    sssp_collect_kernel(const edge_t* __restrict__ offsets, unsigned n_local, const float* __restrict__ reduced,
+                        float* __restrict__ dist_local, int* __restrict__ active_list, b200::counter_t* counts) {
+  __shared__ b200::counter_t sm[256 / 32 + 4];
+  b200::counter_t edges = 0;
+  const unsigned per_cta = 256 * 4;
+  for (unsigned base = blockIdx.x * per_cta; base < n_local; base += gridDim.x * per_cta) {
+    const unsigned first = base + threadIdx.x * 4;
+    int rows[4];
+    unsigned keep = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned v = first + i;
+      rows[i] = int(v);
+      if (v < n_local) {
+        const float r = reduced[v];
+        if (r < dist_local[v]) {
+          dist_local[v] = r;
+          keep |= 1u << i;
+          edges += b200::counter_t(offsets[v + 1] - offsets[v]);
+        }
+      }
+    }
+    b200::cta_append<256, 4>(rows, keep, active_list, counts, b200::counter_t(n_local), sm);
+  }
+  edges = b200::warp_sum(edges);
+  if (b200::lane_id() == 0 && edges) atomicAdd(counts + 1, edges);
+}
+
+template <typename graph_t>
+int partition_collect(ess_context_t ctx, graph_t& G, const float* d_reduced, float* d_dist_local,
+                      int32_t* d_active_list, int64_t* d_counts) {
+  auto* c = ctx->single();
+  const unsigned n_local = unsigned(G.get_number_of_vertices());
+  if (n_local == 0) return 0;
+  c->profiler().begin(gcuda::profiler_t::dense_state, c->stream());
+  sssp_collect_kernel<<<gcuda::persistent_grid(*c, (std::size_t(n_local) + 1023) / 1024, 8), 256, 0, c->stream()>>>(
+      graph::adjacency_of<false>(G).offsets, n_local, d_reduced, d_dist_local, d_active_list,
+      reinterpret_cast<b200::counter_t*>(d_counts));
+  c->profiler().end(c->stream(), 1);
+  error::check_last("partition collect");
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -376,6 +460,8 @@ struct nccl_api_t {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                                cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -397,13 +483,15 @@ nccl_api_t& nccl() {
     api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
     api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
     api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.ReduceScatter = (decltype(api.ReduceScatter))sym("ncclReduceScatter");
     api.Send = (decltype(api.Send))sym("ncclSend");
     api.Recv = (decltype(api.Recv))sym("ncclRecv");
     api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
     api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
     api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
-    api.ok = api.CommInitRank && api.CommDestroy && api.AllGather && api.AllReduce && api.Send && api.Recv &&
+    api.ok = api.CommInitRank && api.CommDestroy && api.AllGather && api.AllReduce && api.ReduceScatter && api.Send &&
+             api.Recv &&
              api.GroupStart && api.GroupEnd && api.GetUniqueId && api.GetErrorString;
   }
   return api;
@@ -460,6 +548,7 @@ struct ess_dist_s {
   unsigned wper = 0, words = 0;
   memory::device_array_t<unsigned> frontier_bits, visited_bits, candidate_bits, isolated_bits, send, recv, a2a_recv;
   memory::device_array_t<int> depth_local, fresh_list;
+  memory::device_array_t<float> replica, dist_local;  // SSSP state, allocated by the first ess_dist_sssp
   memory::device_array_t<long long> counts_dev;
   long long* counts_host = nullptr;  // pinned
   int levels = 0, pull_levels = 0;
@@ -469,6 +558,27 @@ struct ess_dist_s {
     if (comm && nccl().CommDestroy) nccl().CommDestroy(comm);
   }
 };
+
+extern "C" {
+
+int ess_sssp_partition_relax(ess_context_t ctx, ess_graph_t g, const int32_t* d_active_list, int64_t active_count,
+                             const float* d_dist_local, float* d_replica) {
+  ESS_TRY
+  if (!ctx || !g || !d_dist_local || !d_replica) return ess::fail("ess_sssp_partition_relax: null argument");
+  ESS_WITH_GRAPH(g, G, { return partition_relax(ctx, G, d_active_list, active_count, d_dist_local, d_replica); })
+  ESS_CATCH
+}
+
+int ess_sssp_partition_collect(ess_context_t ctx, ess_graph_t g, const float* d_reduced, float* d_dist_local,
+                               int32_t* d_active_list, int64_t* d_counts) {
+  ESS_TRY
+  if (!ctx || !g || !d_reduced || !d_dist_local || !d_active_list || !d_counts)
+    return ess::fail("ess_sssp_partition_collect: null argument");
+  ESS_WITH_GRAPH(g, G, { return partition_collect(ctx, G, d_reduced, d_dist_local, d_active_list, d_counts); })
+  ESS_CATCH
+}
+
+}  // extern "C"
 
 extern "C" {
 
@@ -660,6 +770,86 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
   d->bytes_exchanged = exchanged;
   ess::fill_info(info, ms, level, pulls, level - pulls);
   if (info) info->reserved[0] = exchanged;
+  return 0;
+  ESS_CATCH
+}
+
+/// Start state of one partitioned SSSP: every rank knows dist(source) = 0; the owner seeds its active list.
+static __global__ void sssp_seed_kernel(long long source, long long row_begin, unsigned n_local, float* replica,
+                                        float* dist_local, int* active_list) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  replica[source] = 0.f;
+  const long long local = source - row_begin;
+  if (local >= 0 && local < (long long)n_local) {
+    dist_local[local] = 0.f;
+    active_list[0] = int(local);
+  }
+}
+
+int ess_dist_sssp(ess_dist_t d, int64_t source, ess_run_info* info) {
+  ESS_TRY
+  if (!d) return ess::fail("ess_dist_sssp: null handle");
+  if (source < 0 || source >= d->n_global) return ess::fail("ess_dist_sssp: source out of range");
+  auto* c = d->ctx->single();
+  auto stream = c->stream();
+  auto& api = nccl();
+  ess_graph_t g = d->graph;
+  const int world = d->world, rank = d->rank;
+  const std::size_t per = std::size_t(d->per), n = std::size_t(d->n_global);
+  d->replica.resize(n);
+  d->dist_local.resize(per);
+  float* replica = d->replica.data();
+  float* owned = replica + std::size_t(rank) * per;  // the reduce_scatter lands here (in place)
+  float* dist_local = d->dist_local.data();
+  int* active = d->fresh_list.data();
+  long long* counts = d->counts_dev.data();  // [0..1] this rank, [2..3] all ranks
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  cudaEventRecord(t0, stream);
+  const float inf = gunrock::numeric_limits<float>::max();
+  b200::kernels::fill_kernel<<<gcuda::persistent_grid(*c, (n + 255) / 256, 8), 256, 0, stream>>>(replica, n, inf);
+  b200::kernels::fill_kernel<<<gcuda::persistent_grid(*c, (per + 255) / 256, 8), 256, 0, stream>>>(dist_local, per, inf);
+  sssp_seed_kernel<<<1, 32, 0, stream>>>(source, d->row_begin, unsigned(per), replica, dist_local, active);
+  long long my_count = (source >= d->row_begin && source < d->row_begin + d->per) ? 1 : 0;
+  long long total = 1, relaxed = 0, exchanged = 0;
+  int rounds = 0;
+  while (total > 0) {
+    ++rounds;
+    ESS_WITH_GRAPH(g, G, { partition_relax(d->ctx, G, active, my_count, dist_local, replica); })
+    nccl_check(api.ReduceScatter(replica, owned, per, ncclFloat, ncclMin, d->comm, stream), "reduce_scatter");
+    exchanged += (long long)(world - 1) * (long long)per * 4;
+    cudaMemsetAsync(counts, 0, 2 * sizeof(long long), stream);
+    ESS_WITH_GRAPH(g, G, { partition_collect(d->ctx, G, owned, dist_local, active, reinterpret_cast<int64_t*>(counts)); })
+    nccl_check(api.AllReduce(counts, counts + 2, 2, ncclInt64, ncclSum, d->comm, stream), "allreduce counts");
+    cudaMemcpyAsync(d->counts_host, counts, 4 * sizeof(long long), cudaMemcpyDeviceToHost, stream);
+    error::throw_if_exception(cudaStreamSynchronize(stream), "dist sssp round");  // the one host sync of the round
+    my_count = d->counts_host[0];
+    total = d->counts_host[2];
+    relaxed += d->counts_host[3];
+  }
+  cudaEventRecord(t1, stream);
+  cudaEventSynchronize(t1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, t0, t1);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  ess::fill_info(info, ms, rounds);
+  if (info) {
+    info->reserved[0] = exchanged;
+    info->reserved[1] = relaxed;
+  }
+  return 0;
+  ESS_CATCH
+}
+
+int ess_dist_copy_dist(ess_dist_t d, float* d_out) {
+  ESS_TRY
+  if (!d || !d_out) return ess::fail("ess_dist_copy_dist: null argument");
+  if (d->dist_local.size() != std::size_t(d->per)) return ess::fail("ess_dist_copy_dist: no SSSP has run");
+  error::throw_if_exception(cudaMemcpyAsync(d_out, d->dist_local.data(), std::size_t(d->per) * sizeof(float),
+                                            cudaMemcpyDeviceToDevice, d->ctx->single()->stream()),
+                            "ess_dist_copy_dist");
   return 0;
   ESS_CATCH
 }

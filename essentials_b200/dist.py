@@ -79,6 +79,19 @@ class CudaBackend:
                                             ess._p(next_slice), ess._p(depth_local), ess._p(fresh_list),
                                             ess._p(counts)), "ess_bfs_absorb")
 
+    # ---- SSSP ----
+    def relax(self, active_list, active_count: int, dist_local, replica):
+        ess = self.ess
+        ess._check(ess.lib().ess_sssp_partition_relax(self.ctx.handle, self.graph.handle, ess._p(active_list),
+                                                      int(active_count), ess._p(dist_local), ess._p(replica)),
+                   "ess_sssp_partition_relax")
+
+    def collect(self, reduced, dist_local, active_list, counts):
+        ess = self.ess
+        ess._check(ess.lib().ess_sssp_partition_collect(self.ctx.handle, self.graph.handle, ess._p(reduced),
+                                                        ess._p(dist_local), ess._p(active_list), ess._p(counts)),
+                   "ess_sssp_partition_collect")
+
     def launches(self) -> int:
         return self.ctx.launches()
 
@@ -249,6 +262,73 @@ class PartitionedBFS:
         return out
 
 
+FLT_MAX = 3.4028234663852886e38
+
+
+class PartitionedSSSP:
+    """SSSP over the same 1-D partition (module docstring): label-correcting rounds with a replicated array of
+    tentative distances. Per round: local relax (atomic min into the replica) -> reduce_scatter(min), which
+    hands every owner the best candidate of its rows ((P-1)/P * 4n bytes received per rank) -> the owner
+    collects the rows that improved into its next active list; a 2-word all_reduce carries the global count.
+    Same fixed point as gunrock::sssp::run (reference include/gunrock/algorithms/sssp.hxx:110-136), so the
+    distances are bit-exact with the single-GPU run and the CPU oracle for non-negative weights."""
+
+    def __init__(self, csr_local, row_begin: int, n_global: int, rank: int, world: int, backend, device):
+        assert n_global % world == 0
+        self.rank, self.world, self.device, self.backend = rank, world, device, backend
+        self.n_global, self.per, self.row_begin = n_global, n_global // world, row_begin
+        assert row_begin == rank * self.per and csr_local.offsets.numel() - 1 == self.per
+        self.replica = torch.empty(n_global, dtype=torch.float32, device=device)
+        self.dist_local = torch.empty(self.per, dtype=torch.float32, device=device)
+        self.active = torch.zeros(self.per, dtype=torch.int32, device=device)
+        self.counts = torch.zeros(2, dtype=torch.int64, device=device)
+        self.deg_local = (csr_local.offsets[1:] - csr_local.offsets[:-1]).to(torch.int64)
+        self.rounds = 0
+        self.bytes_exchanged = 0
+        self.relaxed = 0
+
+    def sssp(self, source: int) -> dict:
+        lo = self.row_begin
+        owned = self.replica[lo: lo + self.per]
+        self.replica.fill_(FLT_MAX)
+        self.dist_local.fill_(FLT_MAX)
+        self.replica[source] = 0.0
+        my_count = 0
+        if lo <= source < lo + self.per:
+            self.dist_local[source - lo] = 0.0
+            self.active[0] = source - lo
+            my_count = 1
+        total, rounds, exchanged, relaxed = 1, 0, 0, 0
+        dense_reduce = dist.get_backend() == "gloo"  # gloo has no reduce_scatter: the CPU tests all_reduce
+        while total > 0:
+            rounds += 1
+            self.backend.relax(self.active, my_count, self.dist_local, self.replica)
+            if dense_reduce:
+                dist.all_reduce(self.replica, op=dist.ReduceOp.MIN)
+            else:
+                dist.reduce_scatter_tensor(owned, self.replica, op=dist.ReduceOp.MIN)
+            exchanged += (self.world - 1) * self.per * 4
+            self.counts.zero_()
+            self.backend.collect(owned, self.dist_local, self.active, self.counts)
+            both = torch.cat([self.counts, self.counts])
+            dist.all_reduce(both[2:])
+            my_count, _, total, edges = (int(x) for x in both.tolist())  # the one host sync of the round
+            relaxed += edges
+        self.rounds, self.bytes_exchanged, self.relaxed = rounds, exchanged, relaxed
+        return {"iterations": rounds, "nvlink_bytes_received": exchanged, "relaxed_edges": relaxed, "enact_ms": 0.0}
+
+    def gather_dist(self) -> torch.Tensor:
+        full = torch.empty(self.n_global, dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(full, self.dist_local)
+        return full
+
+    def reached_work(self):
+        r = self.dist_local != FLT_MAX
+        t = torch.stack([r.sum().to(torch.int64), self.deg_local[r].sum()])
+        dist.all_reduce(t)
+        return int(t[0]), int(t[1])
+
+
 class NativePartitionedBFS:
     """The same partitioned BFS with the whole level loop in C++ and NCCL called directly (ess_dist_bfs):
     no Python or torch dispatch on the per-level critical path. Mirrors PartitionedBFS's interface."""
@@ -293,6 +373,33 @@ class NativePartitionedBFS:
         return {"iterations": self.levels, "pull_steps": self.pull_levels, "push_steps": int(info.push_steps),
                 "nvlink_bytes_received": self.bytes_exchanged, "enact_ms": float(info.enact_ms)}
 
+    def sssp(self, source: int) -> dict:
+        """Partitioned SSSP with the round loop in C++ (ess_dist_sssp); distances via gather_dist()."""
+        ess = self.ess
+        info = ess.RunInfo()
+        ess._check(ess.lib().ess_dist_sssp(self.handle, int(source), byref(info)), "ess_dist_sssp")
+        return {"iterations": int(info.iterations), "nvlink_bytes_received": int(info.reserved[0]),
+                "relaxed_edges": int(info.reserved[1]), "enact_ms": float(info.enact_ms)}
+
+    def _fetch_dist(self):
+        if getattr(self, "dist_local", None) is None:
+            self.dist_local = torch.empty(self.per, dtype=torch.float32, device=self.device)
+        self.ess._check(self.ess.lib().ess_dist_copy_dist(self.handle, self.ess._p(self.dist_local)),
+                        "ess_dist_copy_dist")
+
+    def gather_dist(self) -> torch.Tensor:
+        self._fetch_dist()
+        full = torch.empty(self.n_global, dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(full, self.dist_local)
+        return full
+
+    def reached_work_sssp(self):
+        self._fetch_dist()
+        r = self.dist_local != FLT_MAX
+        t = torch.stack([r.sum().to(torch.int64), self.deg_local[r].sum()])
+        dist.all_reduce(t)
+        return int(t[0]), int(t[1])
+
     def _fetch_depth(self):
         """Copy the library-owned depth slice into self.depth_local (device to device, on the context's stream)."""
         self.ess._check(self.ess.lib().ess_dist_copy_depth(self.handle, self.ess._p(self.depth_local)),
@@ -334,7 +441,7 @@ def _pack_bits(flags: torch.Tensor) -> torch.Tensor:
 
 
 def build_partitioned(scale: int, edge_factor: int, rank: int, world: int, device, stream=None, seed: int = 1,
-                      native: bool = True):
+                      native: bool = True, weights: str = "none"):
     """Product constructor: regenerate the counter-based Kronecker edge list, keep this rank's rows, bind the
     CUDA backend. native=True drives the level loop from C++ with NCCL (ess_dist_bfs); False keeps the
     torch.distributed loop of PartitionedBFS."""
@@ -343,7 +450,8 @@ def build_partitioned(scale: int, edge_factor: int, rank: int, world: int, devic
     per = n // world
     ctxmgr = torch.cuda.stream(stream) if stream is not None else _null()
     with ctxmgr:
-        csr = gg.rmat_csr(scale, edge_factor, seed=seed, device=device, row_range=(rank * per, (rank + 1) * per))
+        csr = gg.rmat_csr(scale, edge_factor, seed=seed, device=device, row_range=(rank * per, (rank + 1) * per),
+                          weights=weights)
         if native:
             return NativePartitionedBFS(csr, rank * per, n, rank, world, device, stream)
         backend = CudaBackend(csr, rank * per, n, device, stream if stream is not None else torch.cuda.current_stream())

@@ -222,6 +222,26 @@ ESS_API int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, 
 ESS_API int ess_dist_depth_local(ess_dist_t d, int32_t** d_depth_local, int64_t* count);
 ESS_API int ess_dist_copy_depth(ess_dist_t d, int32_t* d_out); /* owned depth slice -> caller buffer, on the stream */
 
+/* ---- multi-GPU SSSP on the same partition (weights in the graph's values; NULL values = weight 1) --------
+ * Same fixed point as gunrock::sssp::run (include/gunrock/algorithms/sssp.hxx:110-136: relax with atomic min,
+ * keep what improved). Every rank holds a full-length replica of tentative distances: owned entries are exact
+ * after each exchange, the rest are this rank's best candidates so far. One relaxation round =
+ *   ess_sssp_partition_relax   replica[nbr] = min(replica[nbr], dist_local[src] + w) over the out-edges of the
+ *                              active rows (LOCAL ids); enqueue only
+ *   reduce_scatter(min)        of the replica: each owner receives the best candidate of its rows (caller's job:
+ *                              ncclReduceScatter in place, or torch.distributed)
+ *   ess_sssp_partition_collect rows with reduced[v] < dist_local[v] adopt it and are appended to d_active_list;
+ *                              d_counts[0] += rows, d_counts[1] += their out-degrees (two int64 the caller zeroes).
+ * ess_dist_sssp runs the whole loop natively with NCCL; info->iterations = rounds, reserved[0] = bytes received
+ * per rank, reserved[1] = edges relaxed (all ranks). Distances of the owned rows: ess_dist_copy_dist
+ * (FLT_MAX = unreachable). */
+ESS_API int ess_sssp_partition_relax(ess_context_t ctx, ess_graph_t g, const int32_t* d_active_list,
+                                     int64_t active_count, const float* d_dist_local, float* d_replica);
+ESS_API int ess_sssp_partition_collect(ess_context_t ctx, ess_graph_t g, const float* d_reduced, float* d_dist_local,
+                                       int32_t* d_active_list, int64_t* d_counts);
+ESS_API int ess_dist_sssp(ess_dist_t d, int64_t source, ess_run_info* info);
+ESS_API int ess_dist_copy_dist(ess_dist_t d, float* d_out);
+
 #ifdef __cplusplus
 }
 #endif

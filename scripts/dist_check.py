@@ -1,4 +1,4 @@
-"""Multi-GPU parity check (run under torchrun, one rank per GPU): partitioned BFS == single-GPU BFS.
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): partitioned BFS / SSSP == single-GPU result.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
       scripts/dist_check.py --scale 20
@@ -20,40 +20,90 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=int, default=20)
 ap.add_argument("--sources", type=int, default=4)
 ap.add_argument("--python-loop", action="store_true", help="use the torch.distributed level loop instead of ess_dist_bfs")
+ap.add_argument("--alg", default="bfs", help="bfs, sssp or bfs,sssp (one graph build for both)")
+ap.add_argument("--no-check", action="store_true", help="timing only (scales whose full graph does not fit one GPU)")
 args = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-runner = edist.build_partitioned(args.scale, 16, rank, world, dev, native=not args.python_loop)
+algs = args.alg.split(",")
+weights = "hash" if "sssp" in algs else "none"
+runner = edist.build_partitioned(args.scale, 16, rank, world, dev, native=not args.python_loop, weights=weights)
 srcs = runner.pick_sources(args.sources)
 ok = True
-if rank == 0:
-    full = gg.rmat_csr(args.scale, device=dev)
+if rank == 0 and not args.no_check:
+    full = gg.rmat_csr(args.scale, device=dev, weights=weights)
     ctx, g = ess.Context(local), ess.Graph(full)
     assert srcs == gg.pick_sources(full, args.sources)
-for s in [0] + srcs:
-    torch.cuda.synchronize()
-    t = time.time()
-    info = runner.bfs(s)
-    torch.cuda.synchronize()
-    ms = (time.time() - t) * 1e3
-    depth = runner.gather_depth()
-    if rank == 0:
-        want, _ = ess.bfs(ctx, g, s, lb="merge_path", direction="optimized")
-        same = bool(torch.equal(want, depth))
-        ok &= same
-        print(f"src={s} levels={info['iterations']} pull={info['pull_steps']} wall={ms:.2f} ms "
-              f"device={info['enact_ms']:.2f} ms equal={same}", flush=True)
-trace = []
-runner.bfs(srcs[-1], trace=trace)
-if rank == 0 and trace:
-    import collections
-    agg = collections.OrderedDict()
-    for lvl, phase, dt in trace:
-        agg.setdefault(phase, []).append(dt * 1e6)
-    print("phase breakdown (us, per level, synchronised after each phase): " +
-          "; ".join(f"{k}: n={len(v)} avg={sum(v)/len(v):.0f} max={max(v):.0f}" for k, v in agg.items()), flush=True)
+
+
+def check_sssp():
+    """Partitioned SSSP (native loop, or the torch.distributed loop of PartitionedSSSP over the same backend)."""
+    global ok
+    solver = runner
+    if args.python_loop:
+        solver = edist.PartitionedSSSP(runner.csr, runner.row_begin, runner.n_global, rank, world, runner.backend, dev)
+    per_source = []
+    for s in [0] + srcs:
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = time.time()
+        info = solver.sssp(s)
+        torch.cuda.synchronize()
+        ms = (time.time() - t) * 1e3
+        n_r, m_r = solver.reached_work() if args.python_loop else solver.reached_work_sssp()
+        line = (f"src={s} rounds={info['iterations']} wall={ms:.2f} ms device={info['enact_ms']:.2f} ms "
+                f"reached={n_r} m'={m_r} relaxed={info['relaxed_edges']} "
+                f"GTEPS={m_r / max(ms, 1e-9) / 1e6:.2f} recvMB={info['nvlink_bytes_received'] / 1e6:.1f}")
+        if not args.no_check:
+            got = solver.gather_dist()
+            if rank == 0:
+                want, winfo = ess.sssp(ctx, g, s, lb="merge_path")
+                same = bool(torch.equal(want, got))
+                ok &= same
+                line += f" equal={same} single_gpu_ms={winfo['enact_ms']:.2f}"
+        if rank == 0:
+            print(line, flush=True)
+        per_source.append(ms)
+
+
+def check_bfs():
+    global ok
+    for s in [0] + srcs:
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = time.time()
+        info = runner.bfs(s)
+        torch.cuda.synchronize()
+        ms = (time.time() - t) * 1e3
+        n_r, m_r = runner.reached_work()
+        line = (f"src={s} levels={info['iterations']} pull={info['pull_steps']} wall={ms:.2f} ms "
+                f"device={info['enact_ms']:.2f} ms m'={m_r} GTEPS={m_r / max(ms, 1e-9) / 1e6:.2f}")
+        if not args.no_check:
+            depth = runner.gather_depth()
+            if rank == 0:
+                want, _ = ess.bfs(ctx, g, s, lb="merge_path", direction="optimized")
+                same = bool(torch.equal(want, depth))
+                ok &= same
+                line += f" equal={same}"
+        if rank == 0:
+            print(line, flush=True)
+    trace = []
+    runner.bfs(srcs[-1], trace=trace)
+    if rank == 0 and trace:
+        import collections
+        agg = collections.OrderedDict()
+        for lvl, phase, dt in trace:
+            agg.setdefault(phase, []).append(dt * 1e6)
+        print("phase breakdown (us, per level, synchronised after each phase): " +
+              "; ".join(f"{k}: n={len(v)} avg={sum(v)/len(v):.0f} max={max(v):.0f}" for k, v in agg.items()), flush=True)
+
+
+if "bfs" in algs:
+    check_bfs()
+if "sssp" in algs:
+    check_sssp()
 flag = torch.tensor([int(ok)], device=dev)
 dist.broadcast(flag, 0)
 dist.destroy_process_group()

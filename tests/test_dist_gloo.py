@@ -19,6 +19,7 @@ class NumpyBackend:
     def __init__(self, csr_local, row_begin, n_global):
         self.off = csr_local.offsets.numpy().astype(np.int64)
         self.col = csr_local.indices.numpy()
+        self.val = csr_local.values.numpy() if csr_local.values is not None else None
         self.row_begin, self.n_global, self.n_local = row_begin, n_global, self.off.size - 1
 
     @staticmethod
@@ -92,6 +93,67 @@ class NumpyBackend:
         deg = np.diff(self.off)
         counts.view(torch.int64)[0] += int(fresh.sum())
         counts.view(torch.int64)[1] += int(deg[fresh].sum())
+
+
+    # ---- SSSP stand-ins (contract of ess_sssp_partition_relax / ess_sssp_partition_collect) ----
+    def relax(self, active_list, active_count, dist_local, replica):
+        rep, d = replica.numpy(), dist_local.numpy()
+        for v in active_list.numpy()[:active_count]:
+            lo, hi = self.off[v], self.off[v + 1]
+            cand = (d[v] + self.val[lo:hi]).astype(np.float32)  # float32 add, as the device does
+            np.minimum.at(rep, self.col[lo:hi], cand)
+
+    def collect(self, reduced, dist_local, active_list, counts):
+        r, d = reduced.numpy(), dist_local.numpy()
+        ids = np.nonzero(r < d)[0]
+        d[ids] = r[ids]
+        active_list[: ids.size] = torch.from_numpy(ids.astype(np.int32))
+        counts[0] += int(ids.size)
+        counts[1] += int(np.diff(self.off)[ids].sum())
+
+
+def _sssp_worker(rank, world, port, scale, sources, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 1 << scale
+        per = n // world
+        csr = gg.rmat_csr(scale, row_range=(rank * per, (rank + 1) * per), weights="hash")
+        runner = edist.PartitionedSSSP(csr, rank * per, n, rank, world, NumpyBackend(csr, rank * per, n),
+                                       torch.device("cpu"))
+        results = {}
+        for s in sources:
+            info = runner.sssp(s)
+            results[s] = (runner.gather_dist().numpy().copy(), info, runner.reached_work())
+        if rank == 0:
+            out.put(results)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_partitioned_sssp_matches_oracle(world):
+    scale = 9
+    full = gg.rmat_csr(scale, weights="hash")
+    off, col, val = full.host()
+    sources = [0, int(torch.nonzero(full.degrees() == 0)[0])] + gg.pick_sources(full, 2)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sssp_worker, args=(r, world, port, scale, sources, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = out.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    deg = np.diff(off)
+    for s, (got, info, (n_r, m_r)) in results.items():
+        want = oracle.sssp(off, col, val, s)
+        assert np.array_equal(got, want), f"source {s}"  # bit-exact: unique fixed point of float32 min-plus
+        reached = want != np.float32(3.4028234663852886e38)
+        assert n_r == int(reached.sum()) and m_r == int(deg[reached].sum())
+        assert info["iterations"] >= 1 and info["relaxed_edges"] >= m_r - int(deg[s] == 0)
 
 
 def _worker(rank, world, port, scale, sources, out):
