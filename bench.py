@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--lb", default="merge_path")
     ap.add_argument("--direction", default="optimized")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="multi-GPU: NCCL send/recv + all_gather instead of the peer-memory exchange kernels")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the SSSP-grid / PageRank / reference-GPU side runs")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall budget of the reference arm")
@@ -188,6 +190,8 @@ def run_b200(args, rank, world, local_rank):
     if distributed:
         from essentials_b200 import dist as edist
         runner = edist.build_partitioned(args.scale, args.edge_factor, rank, world, dev, stream)
+        if args.nccl_exchange:
+            ess.tune("dist_peer_exchange", 0)
         stream.synchronize()
         n, m, offset_bits = runner.n_global, runner.m_global, runner.offset_bits
         with torch.cuda.stream(stream):
@@ -348,8 +352,12 @@ def run_b200(args, rank, world, local_rank):
                 out["other_configs"] = {"error": repr(e)[:300]}
     else:
         # ---- multi-GPU: NVLink-side accounting + e2e with this rank's partition in host memory ---------
+        kind = runner.exchange_kind() if hasattr(runner, "exchange_kind") else "nccl"
+        how = ("the library's own peer-memory kernels: 8-byte stores into the receivers' IPC-mapped windows over "
+               "NVLink + epoch flags (NCCL only bootstraps)" if kind == "peer-memory" else "NCCL over NVLink")
         out["config"]["exchange"] = ("per level: all_to_all of candidate bitmap slices (top-down levels only) + one "
-                                     "all_gather of the next-frontier slice and Beamer counters; NCCL over NVLink")
+                                     "all_gather of the next-frontier slice and Beamer counters; " + how)
+        out["config"]["exchange_kind"] = kind
         out["config"]["levels"] = runner.levels
         out["config"]["pull_levels"] = runner.pull_levels
         nv_bytes = runner.bytes_exchanged  # received per rank in the last BFS

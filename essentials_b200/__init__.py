@@ -87,6 +87,7 @@ _SIGNATURES = {
     "ess_dist_destroy": (c_int, [c_void_p]),
     "ess_dist_bfs": (c_int, [c_void_p, c_int64, c_float, c_float, POINTER(RunInfo)]),
     "ess_dist_copy_depth": (c_int, [c_void_p, c_void_p]),
+    "ess_dist_exchange_kind": (c_int, [c_void_p, POINTER(c_int)]),
     "ess_dist_sssp": (c_int, [c_void_p, c_int64, POINTER(RunInfo)]),
     "ess_dist_copy_dist": (c_int, [c_void_p, c_void_p]),
     "ess_sssp_partition_relax": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -27,6 +27,10 @@ using graph_of = graph::graph_t<memory::memory_space_t::device, vertex_t, edge_t
 std::string& last_error();
 int fail(const std::exception& e);
 int fail(const char* message, int code = 999);
+/// ess_tune("dist_peer_exchange"): 1 = the partitioned BFS exchanges its bitmaps with its own peer-memory
+/// kernels when the IPC window could be mapped (default), 0 = NCCL collectives.
+int& dist_peer_exchange();
+int& dist_trace();  ///< ess_tune("dist_trace"): per-phase event timing of ess_dist_bfs on stderr (rank 0)
 
 }  // namespace ess
 

@@ -22,6 +22,17 @@ int fail(const char* message, int code) {
 
 using namespace gunrock;
 
+namespace ess {
+int& dist_peer_exchange() {
+  static int on = 1;
+  return on;
+}
+int& dist_trace() {
+  static int on = 0;
+  return on;
+}
+}  // namespace ess
+
 extern "C" {
 
 const char* ess_last_error(void) { return ess::last_error().c_str(); }
@@ -65,6 +76,14 @@ int ess_tune(const char* knob, int value) {
   }
   if (k == "pull_hints") {
     gunrock::operators::advance::kernels::pull_hints_enabled() = value;
+    return 0;
+  }
+  if (k == "dist_trace") {
+    ess::dist_trace() = value;
+    return 0;
+  }
+  if (k == "dist_peer_exchange") {
+    ess::dist_peer_exchange() = value;
     return 0;
   }
   return ess::fail("ess_tune: unknown knob");

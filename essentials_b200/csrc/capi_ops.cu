@@ -537,6 +537,82 @@ __global__ void seed_kernel(const edge_t* __restrict__ offsets, long long source
   }
 }
 
+
+// ---- peer-memory exchange (NVLink loads/stores instead of NCCL collectives) --------------------------
+// Every rank exposes one IPC-mapped window: [inbox: P candidate slices][gather 0 | gather 1: P rows of
+// (next-frontier slice | counters)][flags A: P words][flags B: P words]. A sender copies its data straight
+// into the receivers' windows with 8-byte stores and then raises flag[sender] = epoch in each of them (last
+// CTA, after a system-scope fence); the receiver's stream waits on its own flags before the consuming kernel.
+// Epochs only grow, so flags are never reset; the gather area is double-buffered by level parity because a
+// fast peer may already deliver level L+1 while this rank still merges level L.
+constexpr int max_peers = 16;
+struct peers_t {
+  unsigned* base[max_peers];
+};
+
+/// After this thread's stores: fence, count the CTA in; the last CTA publishes `epoch` to every peer's flag word.
+__device__ __forceinline__ void raise_flags_when_grid_done(const peers_t& peers, int world, int rank,
+                                                           std::size_t flag_off, unsigned epoch, unsigned* done) {
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  if (threadIdx.x < unsigned(world)) {
+    volatile unsigned* flag = peers.base[threadIdx.x] + flag_off + rank;
+    *flag = epoch;
+  }
+  if (threadIdx.x == 0) *done = 0;
+}
+
+/// all_to_all: slice p (slice_words words) of `src` lands in peer p's inbox row `rank`.
+static __global__ void __launch_bounds__(256)
+    peer_scatter_kernel(const unsigned* __restrict__ src, peers_t peers, int world, int rank, unsigned slice_words,
+                        std::size_t inbox_off, std::size_t flag_off, unsigned epoch, unsigned* done) {
+  const std::size_t pairs_per_slice = slice_words / 2, total = pairs_per_slice * world;
+  const uint2* in = reinterpret_cast<const uint2*>(src);
+  for (std::size_t i = std::size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += std::size_t(gridDim.x) * blockDim.x) {
+    const int p = int(i / pairs_per_slice);
+    const std::size_t k = i - std::size_t(p) * pairs_per_slice;
+    reinterpret_cast<uint2*>(peers.base[p] + inbox_off + std::size_t(rank) * slice_words)[k] = in[i];
+  }
+  raise_flags_when_grid_done(peers, world, rank, flag_off, epoch, done);
+}
+
+/// all_gather: this rank's row (row_words words) lands in row `rank` of every peer's gather area.
+static __global__ void __launch_bounds__(256)
+    peer_broadcast_kernel(const unsigned* __restrict__ row, peers_t peers, int world, int rank, unsigned row_words,
+                          std::size_t gather_off, std::size_t flag_off, unsigned epoch, unsigned* done) {
+  const std::size_t pairs = row_words / 2, total = pairs * world;
+  const uint2* in = reinterpret_cast<const uint2*>(row);
+  for (std::size_t i = std::size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += std::size_t(gridDim.x) * blockDim.x) {
+    const int p = int(i / pairs);
+    const std::size_t k = i - std::size_t(p) * pairs;
+    reinterpret_cast<uint2*>(peers.base[p] + gather_off + std::size_t(rank) * row_words)[k] = in[k];
+  }
+  raise_flags_when_grid_done(peers, world, rank, flag_off, epoch, done);
+}
+
+/// Stream-side wait: returns once every peer's flag reached `epoch`; gives up after ~4 s (a dead peer must not
+/// hang the box) and reports through *timed_out (mapped host memory).
+static __global__ void peer_wait_kernel(const unsigned* flags, int world, unsigned epoch, unsigned* timed_out) {
+  if (threadIdx.x >= unsigned(world)) return;
+  const volatile unsigned* flag = flags + threadIdx.x;
+  const long long start = clock64();
+  while (int(*flag - epoch) < 0) {
+    if (clock64() - start > 8000000000LL) {
+      *timed_out = 1u + threadIdx.x;
+      break;
+    }
+    __nanosleep(64);
+  }
+  __threadfence_system();
+}
+
 }  // namespace
 
 struct ess_dist_s {
@@ -553,7 +629,20 @@ struct ess_dist_s {
   long long* counts_host = nullptr;  // pinned
   int levels = 0, pull_levels = 0;
   long long bytes_exchanged = 0;
+  // peer-memory window (see peers_t): own allocation + the mapped windows of the other ranks
+  unsigned* window = nullptr;
+  peers_t peers{};
+  bool peer_ready = false;
+  std::size_t inbox_off = 0, gather_off[2] = {0, 0}, flag_off[2] = {0, 0};
+  unsigned epoch = 0;
+  unsigned* done_counter = nullptr;  // device word of raise_flags_when_grid_done
+  unsigned* timed_out = nullptr;     // pinned, mapped
   ~ess_dist_s() {
+    for (int p = 0; p < world && p < max_peers; ++p)
+      if (p != rank && peers.base[p]) cudaIpcCloseMemHandle(peers.base[p]);
+    if (window) cudaFree(window);
+    if (done_counter) cudaFree(done_counter);
+    if (timed_out) cudaFreeHost(timed_out);
     if (counts_host) cudaFreeHost(counts_host);
     if (comm && nccl().CommDestroy) nccl().CommDestroy(comm);
   }
@@ -642,6 +731,50 @@ int ess_dist_create(ess_context_t ctx, ess_graph_t g, int rank, int world, int64
   cudaMemcpyAsync(d->counts_host, d->counts_dev.data(), sizeof(long long), cudaMemcpyDeviceToHost, stream);
   c->synchronize();
   d->m_global = d->counts_host[0];
+  // peer-memory window: allocate, exchange IPC handles through the communicator, map the peers
+  if (world <= max_peers) {
+    const std::size_t row = std::size_t(d->wper) + 4;
+    d->inbox_off = 0;
+    d->gather_off[0] = std::size_t(d->words);
+    d->gather_off[1] = d->gather_off[0] + row * world;
+    d->flag_off[0] = d->gather_off[1] + row * world;
+    d->flag_off[1] = d->flag_off[0] + 32;
+    const std::size_t window_words = d->flag_off[1] + 32;
+    cudaIpcMemHandle_t mine;
+    bool ok = cudaMalloc(&d->window, window_words * sizeof(unsigned)) == cudaSuccess &&
+              cudaMemsetAsync(d->window, 0, window_words * sizeof(unsigned), stream) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine, d->window) == cudaSuccess &&
+              cudaMalloc(&d->done_counter, sizeof(unsigned)) == cudaSuccess &&
+              cudaMemsetAsync(d->done_counter, 0, sizeof(unsigned), stream) == cudaSuccess &&
+              cudaHostAlloc(&d->timed_out, sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess;
+    memory::device_array_t<unsigned char> handles(std::size_t(world + 1) * sizeof(cudaIpcMemHandle_t));
+    std::vector<cudaIpcMemHandle_t> all(world);
+    if (!ok) std::memset(&mine, 0, sizeof(mine));
+    cudaMemcpyAsync(handles.data() + std::size_t(world) * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, stream);
+    nccl_check(nccl().AllGather(handles.data() + std::size_t(world) * sizeof(mine), handles.data(), sizeof(mine), ncclUint8,
+                                d->comm, stream), "allgather ipc handles");
+    cudaMemcpyAsync(all.data(), handles.data(), std::size_t(world) * sizeof(mine), cudaMemcpyDeviceToHost, stream);
+    c->synchronize();
+    for (int p = 0; p < world && ok; ++p) {
+      if (p == rank) {
+        d->peers.base[p] = d->window;
+        continue;
+      }
+      void* mapped = nullptr;
+      ok = cudaIpcOpenMemHandle(&mapped, all[p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      d->peers.base[p] = static_cast<unsigned*>(mapped);
+    }
+    cudaGetLastError();  // a failed mapping only means the NCCL exchange is used
+    // every rank must take the same path: agree on the outcome
+    d->counts_host[0] = ok ? 1 : 0;
+    cudaMemcpyAsync(d->counts_dev.data(), d->counts_host, sizeof(long long), cudaMemcpyHostToDevice, stream);
+    nccl_check(nccl().AllReduce(d->counts_dev.data(), d->counts_dev.data(), 1, ncclInt64, ncclMin, d->comm, stream),
+               "allreduce peer window");
+    cudaMemcpyAsync(d->counts_host, d->counts_dev.data(), sizeof(long long), cudaMemcpyDeviceToHost, stream);
+    c->synchronize();
+    d->peer_ready = d->counts_host[0] == 1;
+    if (d->timed_out) *d->timed_out = 0;
+  }
   *out = d.release();
   return 0;
   ESS_CATCH
@@ -696,8 +829,22 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
   int level = 0, pulls = 0;
   long long exchanged = 0;
 
+  const bool peer = d->peer_ready && ess::dist_peer_exchange() != 0;
+  // ess_tune("dist_trace", 1): CUDA events between the phases of every level, summed and printed by rank 0
+  const bool trace = ess::dist_trace() != 0;
+  static const char* phase_names[] = {"local(push|pull)", "candidates->owners", "absorb", "slice->all", "merge", "host"};
+  std::vector<std::pair<int, cudaEvent_t>> marks;
+  auto mark = [&](int phase) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    marks.emplace_back(phase, e);
+  };
   while (n_f > 0) {
     ++level;
+    mark(-1);
+    const unsigned epoch = ++d->epoch;  // same sequence on every rank: one epoch per level of every run
     if (!pulling) {
       if (double(m_f) > double(m_u) / double(alpha) && n_f > prev_n_f) pulling = true;
     } else if (double(n_f) < double(d->n_global) / double(beta) && n_f < prev_n_f) {
@@ -711,6 +858,7 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
                        d->depth_local.data(), reinterpret_cast<int64_t*>(counts));
       })
       list_is_current = false;
+      mark(0);
     } else {
       if (!list_is_current) {
         auto& scratch = c->scratch();
@@ -724,31 +872,61 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
                        d->candidate_bits.data(), d->fresh_list.data(), my_count);
       })
       list_is_current = true;
-      nccl_check(api.GroupStart(), "group");
-      for (int p = 0; p < world; ++p) {
-        nccl_check(api.Send(d->candidate_bits.data() + std::size_t(p) * wper, wper, ncclUint32, p, d->comm, stream), "send");
-        nccl_check(api.Recv(d->a2a_recv.data() + std::size_t(p) * wper, wper, ncclUint32, p, d->comm, stream), "recv");
+      mark(0);
+      if (peer) {  // candidate slices go straight into the owners' inboxes over NVLink
+        peer_scatter_kernel<<<gcuda::persistent_grid(*c, (std::size_t(words) / 2 + 255) / 256, 4), 256, 0, stream>>>(
+            d->candidate_bits.data(), d->peers, world, rank, wper, d->inbox_off, d->flag_off[0], epoch, d->done_counter);
+        peer_wait_kernel<<<1, 32, 0, stream>>>(d->window + d->flag_off[0], world, epoch, d->timed_out);
+        c->profiler().launches_total += 2;
+      } else {
+        nccl_check(api.GroupStart(), "group");
+        for (int p = 0; p < world; ++p) {
+          nccl_check(api.Send(d->candidate_bits.data() + std::size_t(p) * wper, wper, ncclUint32, p, d->comm, stream), "send");
+          nccl_check(api.Recv(d->a2a_recv.data() + std::size_t(p) * wper, wper, ncclUint32, p, d->comm, stream), "recv");
+        }
+        nccl_check(api.GroupEnd(), "group");
       }
-      nccl_check(api.GroupEnd(), "group");
+      mark(1);
+      const unsigned* inbox = peer ? d->window + d->inbox_off : d->a2a_recv.data();
       exchanged += (long long)(world - 1) * wper * 4;
       const unsigned grid = gcuda::persistent_grid(*c, ((std::size_t(d->per) + 31) / 32 + 255) / 256, 8);
       auto* cnt = reinterpret_cast<b200::counter_t*>(counts);
       if (g->offset_bits == 64)
         absorb_kernel<int64_t><<<grid, 256, 0, stream>>>(g->g64.get_row_offsets(), unsigned(d->per), first_word, level,
-                                                          d->a2a_recv.data(), world, wper, d->visited_bits.data(),
+                                                          inbox, world, wper, d->visited_bits.data(),
                                                           next_slice, d->depth_local.data(), d->fresh_list.data(), cnt);
       else
         absorb_kernel<int32_t><<<grid, 256, 0, stream>>>(g->g32.get_row_offsets(), unsigned(d->per), first_word, level,
-                                                          d->a2a_recv.data(), world, wper, d->visited_bits.data(),
+                                                          inbox, world, wper, d->visited_bits.data(),
                                                           next_slice, d->depth_local.data(), d->fresh_list.data(), cnt);
     }
-    nccl_check(api.AllGather(d->send.data(), d->recv.data(), wper + 4, ncclUint32, d->comm, stream), "allgather");
+    if (!pulling) mark(2);
+    const unsigned* gathered = d->recv.data();
+    if (peer) {  // the new frontier slice + counters land in every rank's gather area (double-buffered by epoch parity)
+      const std::size_t area = d->gather_off[epoch & 1];
+      peer_broadcast_kernel<<<gcuda::persistent_grid(*c, (std::size_t(wper + 4) / 2 * world + 255) / 256, 4), 256, 0,
+                              stream>>>(d->send.data(), d->peers, world, rank, wper + 4, area, d->flag_off[1], epoch,
+                                        d->done_counter);
+      peer_wait_kernel<<<1, 32, 0, stream>>>(d->window + d->flag_off[1], world, epoch, d->timed_out);
+      c->profiler().launches_total += 2;
+      gathered = d->window + area;
+    } else {
+      nccl_check(api.AllGather(d->send.data(), d->recv.data(), wper + 4, ncclUint32, d->comm, stream), "allgather");
+    }
     exchanged += (long long)(world - 1) * (wper + 4) * 4;
+    mark(3);
     merge_gathered_kernel<<<gcuda::persistent_grid(*c, (std::size_t(words) + 255) / 256, 8), 256, 0, stream>>>(
-        d->recv.data(), world, wper, d->frontier_bits.data(), d->visited_bits.data(), d->counts_dev.data());
+        gathered, world, wper, d->frontier_bits.data(), d->visited_bits.data(), d->counts_dev.data());
+    mark(4);
     cudaMemcpyAsync(d->counts_host, d->counts_dev.data(), 2 * std::size_t(world) * sizeof(long long),
                     cudaMemcpyDeviceToHost, stream);
+    mark(5);
     error::throw_if_exception(cudaStreamSynchronize(stream), "dist bfs level");  // the one host sync of the level
+    if (peer && *d->timed_out) {
+      const unsigned who = *d->timed_out - 1;
+      *d->timed_out = 0;
+      throw error::exception_t("ess_dist_bfs: peer " + std::to_string(who) + " did not deliver its level data");
+    }
     prev_n_f = n_f;
     n_f = 0;
     m_f = 0;
@@ -763,6 +941,24 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
   cudaEventSynchronize(t1);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, t0, t1);
+  if (trace) {
+    double sum[6] = {0}, gaps = 0;
+    int cnt[6] = {0};
+    for (std::size_t i = 1; i < marks.size(); ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, marks[i - 1].second, marks[i].second);
+      if (marks[i].first >= 0)
+        sum[marks[i].first] += t, cnt[marks[i].first]++;
+      else
+        gaps += t;  // host turn-around between the sync of one level and the first launch of the next
+    }
+    if (rank == 0) {
+      std::fprintf(stderr, "[dist_trace] %d levels %.3f ms:", level, ms);
+      for (int k = 0; k < 6; ++k) std::fprintf(stderr, " %s=%.0fus/%d", phase_names[k], sum[k] * 1e3, cnt[k]);
+      std::fprintf(stderr, " level-gaps=%.0fus\n", gaps * 1e3);
+    }
+    for (auto& m : marks) cudaEventDestroy(m.second);
+  }
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
   d->levels = level;
@@ -852,6 +1048,12 @@ int ess_dist_copy_dist(ess_dist_t d, float* d_out) {
                             "ess_dist_copy_dist");
   return 0;
   ESS_CATCH
+}
+
+int ess_dist_exchange_kind(ess_dist_t d, int* kind) {
+  if (!d || !kind) return ess::fail("ess_dist_exchange_kind: null argument");
+  *kind = d->peer_ready && ess::dist_peer_exchange() != 0 ? 1 : 0;
+  return 0;
 }
 
 int ess_dist_copy_depth(ess_dist_t d, int32_t* d_out) {

@@ -400,6 +400,12 @@ class NativePartitionedBFS:
         dist.all_reduce(t)
         return int(t[0]), int(t[1])
 
+    def exchange_kind(self) -> str:
+        """'peer-memory' (own NVLink store kernels + epoch flags) or 'nccl' — what ess_dist_bfs uses right now."""
+        kind = ctypes.c_int(0)
+        self.ess._check(self.ess.lib().ess_dist_exchange_kind(self.handle, byref(kind)), "ess_dist_exchange_kind")
+        return "peer-memory" if kind.value else "nccl"
+
     def _fetch_depth(self):
         """Copy the library-owned depth slice into self.depth_local (device to device, on the context's stream)."""
         self.ess._check(self.ess.lib().ess_dist_copy_depth(self.handle, self.ess._p(self.depth_local)),

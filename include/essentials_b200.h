@@ -220,6 +220,11 @@ ESS_API int ess_dist_create(ess_context_t ctx, ess_graph_t g, int rank, int worl
 ESS_API int ess_dist_destroy(ess_dist_t d);
 ESS_API int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_info* info);
 ESS_API int ess_dist_depth_local(ess_dist_t d, int32_t** d_depth_local, int64_t* count);
+/* How ess_dist_bfs moves its bitmaps between ranks: 1 = the library's own peer-memory kernels (every rank maps
+ * the others' exchange window with cudaIpcOpenMemHandle at ess_dist_create; a sender stores its slices straight
+ * into the receivers' windows over NVLink and raises an epoch flag, the receiver's stream waits on the flags),
+ * 0 = NCCL send/recv + all_gather (mapping failed, or ess_tune("dist_peer_exchange", 0)). */
+ESS_API int ess_dist_exchange_kind(ess_dist_t d, int* kind);
 ESS_API int ess_dist_copy_depth(ess_dist_t d, int32_t* d_out); /* owned depth slice -> caller buffer, on the stream */
 
 /* ---- multi-GPU SSSP on the same partition (weights in the graph's values; NULL values = weight 1) --------

@@ -20,6 +20,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=int, default=20)
 ap.add_argument("--sources", type=int, default=4)
 ap.add_argument("--python-loop", action="store_true", help="use the torch.distributed level loop instead of ess_dist_bfs")
+ap.add_argument("--nccl-exchange", action="store_true", help="ess_dist_bfs: NCCL collectives instead of peer memory")
+ap.add_argument("--compare-exchange", action="store_true", help="time the BFS sources with both exchanges")
 ap.add_argument("--alg", default="bfs", help="bfs, sssp or bfs,sssp (one graph build for both)")
 ap.add_argument("--no-check", action="store_true", help="timing only (scales whose full graph does not fit one GPU)")
 args = ap.parse_args()
@@ -30,6 +32,10 @@ dist.init_process_group("nccl", device_id=dev)
 algs = args.alg.split(",")
 weights = "hash" if "sssp" in algs else "none"
 runner = edist.build_partitioned(args.scale, 16, rank, world, dev, native=not args.python_loop, weights=weights)
+if args.nccl_exchange:
+    ess.tune("dist_peer_exchange", 0)
+if rank == 0 and hasattr(runner, "exchange_kind"):
+    print(f"exchange: {runner.exchange_kind()}", flush=True)
 srcs = runner.pick_sources(args.sources)
 ok = True
 if rank == 0 and not args.no_check:
@@ -102,6 +108,25 @@ def check_bfs():
 
 if "bfs" in algs:
     check_bfs()
+    if args.compare_exchange:
+        ess.tune("dist_trace", 1)
+        for mode in (1, 0):
+            ess.tune("dist_peer_exchange", mode)
+            for s in srcs[:3]:
+                dist.barrier()
+                torch.cuda.synchronize()
+                runner.bfs(s)
+        ess.tune("dist_trace", 0)
+        for mode in (1, 0, 1, 0):
+            ess.tune("dist_peer_exchange", mode)
+            times = []
+            for s in srcs:
+                dist.barrier()
+                torch.cuda.synchronize()
+                times.append(runner.bfs(s)["enact_ms"])
+            if rank == 0:
+                print(f"exchange={runner.exchange_kind():11s} device ms per source: " +
+                      " ".join(f"{t:.3f}" for t in times) + f"  mean={sum(times) / len(times):.3f}", flush=True)
 if "sssp" in algs:
     check_sssp()
 flag = torch.tensor([int(ok)], device=dev)

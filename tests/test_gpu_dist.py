@@ -11,15 +11,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (CPU gloo test covers the host logic)")
-@pytest.mark.parametrize("loop", ["native", "python"])
+@pytest.mark.parametrize("loop", ["native", "native-nccl", "python"])
 def test_partitioned_bfs_two_gpus(loop):
-    """Both drivers of the 1-D partitioned BFS — ess_dist_bfs (C++ + NCCL) and the torch.distributed loop that the
-    gloo tests cover — must reproduce the single-GPU depths."""
+    """The drivers of the 1-D partitioned BFS — ess_dist_bfs with its peer-memory exchange kernels, the same loop
+    over NCCL collectives, and the torch.distributed loop that the gloo tests cover — must reproduce the
+    single-GPU depths."""
+    port = {"native": "29517", "native-nccl": "29516", "python": "29518"}[loop]
+    extra = {"native": [], "native-nccl": ["--nccl-exchange"], "python": ["--python-loop"]}[loop]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29517" if loop == "native" else "29518",
-           os.path.join(ROOT, "scripts", "dist_check.py"), "--scale", "18"] + (["--python-loop"] if loop == "python" else [])
+           "127.0.0.1", "--master-port", port, os.path.join(ROOT, "scripts", "dist_check.py"), "--scale", "18"] + extra
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DIST_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    if loop.startswith("native"):
+        assert ("exchange: nccl" if loop == "native-nccl" else "exchange: peer-memory") in out.stdout, out.stdout[-2000:]
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (CPU gloo test covers the host logic)")
