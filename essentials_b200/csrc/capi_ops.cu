@@ -90,9 +90,11 @@ int filter_probe(ess_context_t ctx, graph_t& G, const int32_t* d_in, int64_t siz
 template <typename edge_t>
 __global__ void __launch_bounds__(256)
     absorb_kernel(const edge_t* __restrict__ offsets, unsigned n_local, unsigned first_word, int level,
-                  const unsigned* __restrict__ candidates, int n_slices, unsigned slice_stride,
-                  unsigned* __restrict__ visited_bits, unsigned* __restrict__ next_slice, int* __restrict__ depth_local,
-                  int* __restrict__ fresh_list, b200::counter_t* counts) {
+                  unsigned* candidates, int n_slices, unsigned slice_stride, unsigned* __restrict__ visited_bits,
+                  unsigned* __restrict__ next_slice, int* __restrict__ depth_local, int* __restrict__ fresh_list,
+                  b200::counter_t* counts, bool consume) {
+  // consume: zero every non-zero candidate word after reading it — the peer-memory exchange only stores non-zero
+  // words into this inbox, so it must be all-zero again before the next level's senders arrive
   // one THREAD per 32-vertex word (coalesced word streams; a warp-per-word version spent 140 us per level on
   // 1 M mostly empty words at scale-26), one warp-aggregated slot claim per warp trip
   const unsigned n_words = (n_local + 31u) >> 5;
@@ -104,7 +106,11 @@ __global__ void __launch_bounds__(256)
     if (w < n_words) {
       seen = visited_bits[first_word + w];
       unsigned cand = 0;
-      for (int p = 0; p < n_slices; ++p) cand |= candidates[std::size_t(p) * slice_stride + w];
+      for (int p = 0; p < n_slices; ++p) {
+        const unsigned x = candidates[std::size_t(p) * slice_stride + w];
+        if (consume && x) candidates[std::size_t(p) * slice_stride + w] = 0;
+        cand |= x;
+      }
       fresh = cand & ~seen;
       next_slice[w] = fresh;
       if (fresh) visited_bits[first_word + w] = seen | fresh;
@@ -135,21 +141,23 @@ __global__ void __launch_bounds__(256)
 /// After the per-level all_gather: unpack the P rows of (next-frontier slice | 2 x int64 counters) into the
 /// replicated frontier bitmap, fold it into the visited bitmap and collect the counters in one small array.
 static __global__ void __launch_bounds__(256)
-    merge_gathered_kernel(const unsigned* __restrict__ gathered, int world, unsigned slice_words,
-                          unsigned* __restrict__ frontier_bits, unsigned* __restrict__ visited_bits,
-                          long long* __restrict__ counts_out) {
+    merge_gathered_kernel(unsigned* gathered, int world, unsigned slice_words, unsigned* __restrict__ frontier_bits,
+                          unsigned* __restrict__ visited_bits, long long* __restrict__ counts_out, bool consume) {
   const unsigned row = slice_words + 4;
   const std::size_t total = std::size_t(world) * slice_words;
   for (std::size_t w = std::size_t(blockIdx.x) * blockDim.x + threadIdx.x; w < total;
        w += std::size_t(gridDim.x) * blockDim.x) {
     const unsigned r = unsigned(w / slice_words), k = unsigned(w % slice_words);
     const unsigned bits = gathered[std::size_t(r) * row + k];
+    if (consume && bits) gathered[std::size_t(r) * row + k] = 0;  // see absorb_kernel
     frontier_bits[w] = bits;
     if (bits) visited_bits[w] |= bits;
   }
   if (blockIdx.x == 0 && threadIdx.x < 2 * world) {
     const int r = threadIdx.x / 2, c = threadIdx.x % 2;
-    counts_out[threadIdx.x] = reinterpret_cast<const long long*>(gathered + std::size_t(r) * row + slice_words)[c];
+    long long* cell = reinterpret_cast<long long*>(gathered + std::size_t(r) * row + slice_words) + c;
+    counts_out[threadIdx.x] = *cell;
+    if (consume) *cell = 0;
   }
 }
 
@@ -411,8 +419,8 @@ int ess_bfs_merge_gathered(ess_context_t ctx, const uint32_t* d_gathered, int32_
   auto* c = ctx->single();
   const std::size_t total = std::size_t(world) * std::size_t(slice_words);
   merge_gathered_kernel<<<gcuda::persistent_grid(*c, (total + 255) / 256, 8), 256, 0, c->stream()>>>(
-      d_gathered, world, unsigned(slice_words), d_frontier_bits, d_visited_bits,
-      reinterpret_cast<long long*>(d_counts_out));
+      const_cast<uint32_t*>(d_gathered), world, unsigned(slice_words), d_frontier_bits, d_visited_bits,
+      reinterpret_cast<long long*>(d_counts_out), false);
   error::check_last("merge gathered");
   return 0;
   ESS_CATCH
@@ -431,12 +439,14 @@ int ess_bfs_absorb(ess_context_t ctx, ess_graph_t g, int64_t row_begin, int32_t 
   c->profiler().begin(gcuda::profiler_t::dense_state, stream);
   if (g->offset_bits == 64)
     absorb_kernel<int64_t><<<grid, 256, 0, stream>>>(g->g64.get_row_offsets(), n_local, unsigned(row_begin >> 5), level,
-                                                      d_candidates, n_slices, unsigned(slice_stride_words),
-                                                      d_visited_bits, d_next_slice, d_depth_local, d_fresh_list, counts);
+                                                      const_cast<uint32_t*>(d_candidates), n_slices,
+                                                      unsigned(slice_stride_words), d_visited_bits, d_next_slice,
+                                                      d_depth_local, d_fresh_list, counts, false);
   else
     absorb_kernel<int32_t><<<grid, 256, 0, stream>>>(g->g32.get_row_offsets(), n_local, unsigned(row_begin >> 5), level,
-                                                      d_candidates, n_slices, unsigned(slice_stride_words),
-                                                      d_visited_bits, d_next_slice, d_depth_local, d_fresh_list, counts);
+                                                      const_cast<uint32_t*>(d_candidates), n_slices,
+                                                      unsigned(slice_stride_words), d_visited_bits, d_next_slice,
+                                                      d_depth_local, d_fresh_list, counts, false);
   c->profiler().end(stream);
   error::check_last("absorb");
   return 0;
@@ -541,7 +551,8 @@ __global__ void seed_kernel(const edge_t* __restrict__ offsets, long long source
 // ---- peer-memory exchange (NVLink loads/stores instead of NCCL collectives) --------------------------
 // Every rank exposes one IPC-mapped window: [inbox: P candidate slices][gather 0 | gather 1: P rows of
 // (next-frontier slice | counters)][flags A: P words][flags B: P words]. A sender copies its data straight
-// into the receivers' windows with 8-byte stores and then raises flag[sender] = epoch in each of them (last
+// into the receivers' windows with 8-byte stores (only the non-zero ones: receivers clear what they consume, so
+// sparse levels cost almost no NVLink traffic) and then raises flag[sender] = epoch in each of them (last
 // CTA, after a system-scope fence); the receiver's stream waits on its own flags before the consuming kernel.
 // Epochs only grow, so flags are never reset; the gather area is double-buffered by level parity because a
 // fast peer may already deliver level L+1 while this rank still merges level L.
@@ -577,7 +588,9 @@ static __global__ void __launch_bounds__(256)
        i += std::size_t(gridDim.x) * blockDim.x) {
     const int p = int(i / pairs_per_slice);
     const std::size_t k = i - std::size_t(p) * pairs_per_slice;
-    reinterpret_cast<uint2*>(peers.base[p] + inbox_off + std::size_t(rank) * slice_words)[k] = in[i];
+    const uint2 v = in[i];
+    if (v.x | v.y)  // receivers keep their inbox all-zero between levels (absorb_kernel, consume)
+      reinterpret_cast<uint2*>(peers.base[p] + inbox_off + std::size_t(rank) * slice_words)[k] = v;
   }
   raise_flags_when_grid_done(peers, world, rank, flag_off, epoch, done);
 }
@@ -592,7 +605,9 @@ static __global__ void __launch_bounds__(256)
        i += std::size_t(gridDim.x) * blockDim.x) {
     const int p = int(i / pairs);
     const std::size_t k = i - std::size_t(p) * pairs;
-    reinterpret_cast<uint2*>(peers.base[p] + gather_off + std::size_t(rank) * row_words)[k] = in[k];
+    const uint2 v = in[k];
+    if (v.x | v.y)  // receivers zero the area while merging it (merge_gathered_kernel, consume)
+      reinterpret_cast<uint2*>(peers.base[p] + gather_off + std::size_t(rank) * row_words)[k] = v;
   }
   raise_flags_when_grid_done(peers, world, rank, flag_off, epoch, done);
 }
@@ -887,21 +902,23 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
         nccl_check(api.GroupEnd(), "group");
       }
       mark(1);
-      const unsigned* inbox = peer ? d->window + d->inbox_off : d->a2a_recv.data();
+      unsigned* inbox = peer ? d->window + d->inbox_off : d->a2a_recv.data();
       exchanged += (long long)(world - 1) * wper * 4;
       const unsigned grid = gcuda::persistent_grid(*c, ((std::size_t(d->per) + 31) / 32 + 255) / 256, 8);
       auto* cnt = reinterpret_cast<b200::counter_t*>(counts);
       if (g->offset_bits == 64)
         absorb_kernel<int64_t><<<grid, 256, 0, stream>>>(g->g64.get_row_offsets(), unsigned(d->per), first_word, level,
                                                           inbox, world, wper, d->visited_bits.data(),
-                                                          next_slice, d->depth_local.data(), d->fresh_list.data(), cnt);
+                                                          next_slice, d->depth_local.data(), d->fresh_list.data(), cnt,
+                                                          peer);
       else
         absorb_kernel<int32_t><<<grid, 256, 0, stream>>>(g->g32.get_row_offsets(), unsigned(d->per), first_word, level,
                                                           inbox, world, wper, d->visited_bits.data(),
-                                                          next_slice, d->depth_local.data(), d->fresh_list.data(), cnt);
+                                                          next_slice, d->depth_local.data(), d->fresh_list.data(), cnt,
+                                                          peer);
     }
     if (!pulling) mark(2);
-    const unsigned* gathered = d->recv.data();
+    unsigned* gathered = d->recv.data();
     if (peer) {  // the new frontier slice + counters land in every rank's gather area (double-buffered by epoch parity)
       const std::size_t area = d->gather_off[epoch & 1];
       peer_broadcast_kernel<<<gcuda::persistent_grid(*c, (std::size_t(wper + 4) / 2 * world + 255) / 256, 4), 256, 0,
@@ -916,7 +933,7 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
     exchanged += (long long)(world - 1) * (wper + 4) * 4;
     mark(3);
     merge_gathered_kernel<<<gcuda::persistent_grid(*c, (std::size_t(words) + 255) / 256, 8), 256, 0, stream>>>(
-        gathered, world, wper, d->frontier_bits.data(), d->visited_bits.data(), d->counts_dev.data());
+        gathered, world, wper, d->frontier_bits.data(), d->visited_bits.data(), d->counts_dev.data(), peer);
     mark(4);
     cudaMemcpyAsync(d->counts_host, d->counts_dev.data(), 2 * std::size_t(world) * sizeof(long long),
                     cudaMemcpyDeviceToHost, stream);
