@@ -299,6 +299,9 @@ def run_b200(args, rank, world, local_rank):
             "share_of_step": d_ms / ms if ms else None,
             "whole_bfs_effective_gbs": graph500_bytes / (ms * 1e-3) / 1e9,
             "note": "achieved counts bytes the kernel actually has to move (early-exited edges are not counted); "
+                    "traffic (ncu DRAM bytes per launch, mean over every launch of the class) exceeds the algorithmic "
+                    "bytes because each walked vertex costs whole 32-byte sectors for 4-12 useful bytes, not because "
+                    "anything is re-read; "
                     "whole_bfs_effective_gbs uses SURVEY §8d's 8*m'+(2*sE+12)*n' over the step time and can exceed "
                     "the peak because direction optimisation skips most edges",
         }
