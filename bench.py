@@ -418,6 +418,25 @@ def side_runs(args, ctx, csr, graph, timed, work, dev):
                                     "ours_gteps": work[s][1] / info["enact_ms"] / 1e6,
                                     "depths_equal": bool(torch.equal(ours, ref_depth))}
         del ref_depth
+    # SSSP on the bench graph itself (weights from the symmetric pair hash): dense delta variant vs the frontier recipe
+    if csr.symmetric:
+        from dataclasses import replace
+        deg = (csr.offsets[1:] - csr.offsets[:-1]).to(torch.int64)
+        rows = torch.repeat_interleave(torch.arange(csr.n, device=dev, dtype=torch.int64), deg)
+        weighted = replace(csr, values=gg.pair_weights(rows, csr.indices.to(torch.int64)))
+        del rows, deg
+        wg = ess.Graph(weighted)
+        runs = []
+        for s in timed[:3]:
+            for _ in range(2):  # second run: buffers warm
+                d_delta, i_delta = ess.sssp_delta(ctx, wg, s)
+                d_front, i_front = ess.sssp(ctx, wg, s, lb="merge_path")
+            runs.append({"source": s, "delta_enact_ms": i_delta["enact_ms"], "delta_rounds": i_delta["rounds"],
+                         "delta_gteps": work[s][1] / i_delta["enact_ms"] / 1e6,
+                         "frontier_merge_path_enact_ms": i_front["enact_ms"],
+                         "distances_equal": bool(torch.equal(d_delta, d_front))})
+        res["sssp_kron_bench_graph"] = {"weights": "uniform [1,64) dyadic, symmetric hash", "runs": runs}
+        del wg, weighted, d_delta, d_front
     # config 3: SSSP on the 4900 x 4900 grid
     grid = gg.grid_csr(4900, 4900, device=dev)
     gg_graph = ess.Graph(grid)

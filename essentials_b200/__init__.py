@@ -64,6 +64,7 @@ _SIGNATURES = {
     "ess_bfs": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int, c_int, c_float, c_float, POINTER(RunInfo)]),
     "ess_sssp": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int, POINTER(RunInfo)]),
     "ess_sssp_near_far": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_float, POINTER(RunInfo)]),
+    "ess_sssp_delta": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_float, POINTER(RunInfo)]),
     "ess_pagerank": (c_int, [c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_int, c_int, POINTER(RunInfo)]),
     "ess_ppr": (c_int, [c_void_p, c_void_p, c_int32, c_float, c_float, c_void_p, c_int, POINTER(RunInfo)]),
     "ess_kcore": (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(RunInfo)]),
@@ -262,6 +263,19 @@ def sssp_near_far(ctx: Context, g: Graph, source: int, delta: float = 0.0, out=N
            "ess_sssp_near_far")
     d = info.as_dict()
     d.update(levels=int(info.reserved[0]), splits=int(info.reserved[1]), relaxations=int(info.reserved[2]))
+    return dist, d
+
+
+def sssp_delta(ctx: Context, g: Graph, source: int, delta: float = 0.0, out=None):
+    """SSSP through gunrock::sssp::run_delta (dense active set + delta thresholds; for low-diameter graphs)."""
+    import torch
+    dist = _out(g.n, torch.float32, g.csr.indices) if out is None else out
+    info = RunInfo()
+    _check(lib().ess_sssp_delta(ctx.handle, g.handle, int(source), _p(dist), float(delta), byref(info)),
+           "ess_sssp_delta")
+    d = info.as_dict()
+    d.update(rounds=int(info.reserved[0]), threshold_advances=int(info.reserved[1]),
+             expanded_vertices=int(info.reserved[2]), passes=int(info.reserved[3]))
     return dist, d
 
 

@@ -39,3 +39,20 @@ extern "C" int ess_sssp(ess_context_t ctx, ess_graph_t g, int32_t source, float*
   });
   ESS_CATCH
 }
+
+extern "C" int ess_sssp_delta(ess_context_t ctx, ess_graph_t g, int32_t source, float* d_dist, float delta,
+                              ess_run_info* info) {
+  ESS_TRY
+  if (!ctx || !g || !d_dist) return ess::fail("ess_sssp_delta: null argument");
+  if (source < 0 || source >= g->n) return ess::fail("ess_sssp_delta: source out of range");
+  ESS_WITH_GRAPH(g, G, {
+    int iters = 0;
+    long long stats[4] = {0, 0, 0, 0};
+    float ms = sssp::run_delta(G, source, d_dist, ctx->ctx, delta, &iters, stats);
+    ess::fill_info(info, ms, iters);
+    if (info)
+      for (int i = 0; i < 4; ++i) info->reserved[i] = stats[i];
+    return 0;
+  })
+  ESS_CATCH
+}

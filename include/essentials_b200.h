@@ -120,6 +120,14 @@ ESS_API int ess_sssp(ess_context_t ctx, ess_graph_t g, int32_t source, float* d_
 ESS_API int ess_sssp_near_far(ess_context_t ctx, ess_graph_t g, int32_t source, float* d_dist, float delta,
                               ess_run_info* info);
 
+/* Same distances through gunrock::sssp::run_delta (include/gunrock/algorithms/sssp.hxx): a dense active set chosen
+ * per round by one streaming pass (distance dropped since last expansion AND below a threshold that advances by
+ * `delta`), expanded with the merge-path advance. For low-diameter graphs with big frontiers (Kronecker/RMAT),
+ * where it halves the relaxations of plain label-correcting; delta <= 0 picks mean edge weight / 2.
+ * info->iterations = expanding rounds; reserved = {rounds, threshold advances, vertices expanded, passes}. */
+ESS_API int ess_sssp_delta(ess_context_t ctx, ess_graph_t g, int32_t source, float* d_dist, float delta,
+                           ess_run_info* info);
+
 /* gunrock::pr::run — include/gunrock/algorithms/pr.hxx:183-216 (alpha 0.85, tol 1e-6 in examples/algorithms/pr/pr.cu:55-56).
  * pull != 0 gathers over the CSC view instead of scattering with atomics. */
 ESS_API int ess_pagerank(ess_context_t ctx, ess_graph_t g, float alpha, float tol, int max_iterations, float* d_p, int lb,

@@ -165,6 +165,35 @@ def test_sssp_near_far_larger_graphs(ctx):
         assert info["relaxations"] >= grid.m * 0 + 1
 
 
+@pytest.mark.parametrize("delta", [0.0, 0.5, 7.5, 64.0, 3e38])
+def test_sssp_delta_bit_exact(ctx, graphs, golden, delta):
+    """gunrock::sssp::run_delta (dense active set, threshold advancing by delta): reference distances for every
+    bucket width — huge delta is plain label correcting, tiny delta close to Dijkstra order — and n not a
+    multiple of the 4-wide vector loads (chesapeake: 39 vertices)."""
+    for name in ("chesapeake", "rmat_s10", "grid_24x17"):
+        for s in golden[name]["sources"]:
+            dist, info = ess.sssp_delta(ctx, graphs[name], int(s), delta=delta)
+            assert np.array_equal(dist.cpu().numpy(), golden[name][f"sssp_{s}"]), (name, int(s), delta)
+            assert info["passes"] >= info["rounds"] + 1  # the last pass finds nothing left
+
+
+def test_sssp_delta_larger_graph_and_work(ctx):
+    csr = gg.rmat_csr(15, weights="hash", device="cuda")
+    off, col, val = csr.host()
+    g = ess.Graph(csr)
+    for s in gg.pick_sources(csr, 2):
+        want = oracle.sssp(off, col, val, s)
+        plain, i_plain = ess.sssp_delta(ctx, g, s, delta=3e38)
+        near, i_near = ess.sssp_delta(ctx, g, s)
+        assert np.array_equal(plain.cpu().numpy(), want) and np.array_equal(near.cpu().numpy(), want)
+        # thresholds trade rounds for work: more rounds, fewer vertex expansions than plain label correcting
+        assert i_near["rounds"] >= i_plain["rounds"] and i_near["expanded_vertices"] <= i_plain["expanded_vertices"]
+    iso = int(torch.nonzero(csr.degrees() == 0)[0])
+    dist, info = ess.sssp_delta(ctx, g, iso)
+    d = dist.cpu().numpy()
+    assert d[iso] == 0 and (np.delete(d, iso) == np.float32(3.4028234663852886e38)).all() and info["rounds"] == 1
+
+
 # ------------------------------------------------------------------------------------------------ PageRank
 @pytest.mark.parametrize("mode", ["pull", "block_mapped", "merge_path", "bucketing", "thread_mapped"])
 def test_pagerank_directed_rmat(ctx, mode):
