@@ -249,7 +249,7 @@ int partition_step(ess_context_t ctx, graph_t& G, int64_t row_begin, int64_t n_g
 /// Relax the out-edges of this rank's active rows (LOCAL row ids): replica[nbr] = min(replica[nbr], dist[src] + w).
 template <typename graph_t>
 int partition_relax(ess_context_t ctx, graph_t& G, const int32_t* d_active_list, int64_t active_count,
-                    const float* d_dist_local, float* d_replica) {
+                    const float* d_dist_local, float* d_replica, unsigned* d_dirty_chunks = nullptr) {
   using edge_t = typename graph_t::edge_type;
   if (active_count <= 0) return 0;
   auto* c = ctx->single();
@@ -259,10 +259,16 @@ int partition_relax(ess_context_t ctx, graph_t& G, const int32_t* d_active_list,
   static thread_local memory::device_array_t<edge_t> segments;
   const float* dist_local = d_dist_local;
   float* replica = d_replica;
-  auto op = [dist_local, replica] __device__(int32_t const& src, int32_t const& nbr, edge_t const& e,
-                                             float const& w) -> bool {
+  // dirty (optional): one word per 1024 replica entries, raised when an entry of the chunk was lowered — the
+  // owners' fused reduce+collect only fetches chunks a peer actually touched
+  unsigned* dirty = d_dirty_chunks;
+  auto op = [dist_local, replica, dirty] __device__(int32_t const& src, int32_t const& nbr, edge_t const& e,
+                                                    float const& w) -> bool {
     const float nd = dist_local[src] + w;
-    if (nd < replica[nbr]) math::atomic::min(replica + nbr, nd);  // the plain read only prunes
+    if (nd < replica[nbr]) {  // the plain read only prunes
+      const float old = math::atomic::min(replica + nbr, nd);
+      if (dirty && nd < old && !dirty[unsigned(nbr) >> 10]) dirty[unsigned(nbr) >> 10] = 1u;
+    }
     return false;
   };
   using namespace operators;
@@ -628,6 +634,80 @@ static __global__ void peer_wait_kernel(const unsigned* flags, int world, unsign
   __threadfence_system();
 }
 
+
+/// Flag-only signal (no payload pushed): "my kernels before this point are done for epoch".
+static __global__ void peer_signal_kernel(peers_t peers, int world, int rank, std::size_t flag_off, unsigned epoch) {
+  if (threadIdx.x < unsigned(world)) {
+    __threadfence_system();
+    volatile unsigned* flag = peers.base[threadIdx.x] + flag_off + rank;
+    *flag = epoch;
+  }
+}
+
+struct replicas_t {
+  const float* value[max_peers];     ///< every rank's full-length replica of tentative distances
+  const unsigned* dirty[max_peers];  ///< its per-1024-entry dirty words
+};
+
+/// Partitioned SSSP, owner side, exchange and filter in ONE kernel over peer memory: a CTA takes a 1024-row chunk
+/// of the owned range, looks at each peer's dirty word for it, fetches the chunk only from the peers that touched
+/// it (float4 loads over NVLink), takes the minimum with the local candidates, and the rows whose distance dropped
+/// adopt it and join the next active list. Replaces reduce_scatter(min) + sssp_collect_kernel; late rounds, where
+/// few chunks are dirty, move almost nothing.
+template <typename edge_t>
+static __global__ void __launch_bounds__(256)
+    sssp_peer_reduce_collect_kernel(const edge_t* __restrict__ offsets, unsigned n_local, long long row_begin,
+                                    replicas_t reps, int world, int rank, float* replica_self,
+                                    float* __restrict__ dist_local, int* __restrict__ active_list,
+                                    b200::counter_t* counts) {
+  __shared__ unsigned s_dirty[max_peers];
+  __shared__ b200::counter_t sm[256 / 32 + 4];
+  const unsigned chunks = n_local >> 10;  // the caller guarantees n_local % 1024 == 0
+  b200::counter_t edges = 0, fetched = 0;
+  for (unsigned c = blockIdx.x; c < chunks; c += gridDim.x) {
+    const std::size_t global_chunk = std::size_t(row_begin >> 10) + c;
+    if (threadIdx.x < unsigned(world))
+      s_dirty[threadIdx.x] = int(threadIdx.x) == rank ? 0u : reps.dirty[threadIdx.x][global_chunk];
+    __syncthreads();
+    const unsigned v0 = (c << 10) + threadIdx.x * 4;
+    float4 best = *reinterpret_cast<const float4*>(replica_self + row_begin + v0);
+    for (int p0 = 0; p0 < world; p0 += 8) {  // all fetches of a batch in flight before the first min
+      float4 got[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (p0 + k < world && s_dirty[p0 + k])
+          got[k] = *reinterpret_cast<const float4*>(reps.value[p0 + k] + row_begin + v0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (p0 + k < world && s_dirty[p0 + k]) {
+          best.x = fminf(best.x, got[k].x), best.y = fminf(best.y, got[k].y);
+          best.z = fminf(best.z, got[k].z), best.w = fminf(best.w, got[k].w);
+          if (threadIdx.x == 0) ++fetched;
+        }
+    }
+    const float4 cur = *reinterpret_cast<const float4*>(dist_local + v0);
+    const float b[4] = {best.x, best.y, best.z, best.w}, o[4] = {cur.x, cur.y, cur.z, cur.w};
+    int rows[4];
+    unsigned keep = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      rows[i] = int(v0 + i);
+      if (b[i] < o[i]) {
+        keep |= 1u << i;
+        edges += b200::counter_t(offsets[v0 + i + 1] - offsets[v0 + i]);
+      }
+    }
+    if (keep) {
+      *reinterpret_cast<float4*>(dist_local + v0) = best;                 // best <= cur in every lane
+      *reinterpret_cast<float4*>(replica_self + row_begin + v0) = best;   // owned replica entries stay exact
+    }
+    b200::cta_append<256, 4>(rows, keep, active_list, counts, b200::counter_t(n_local), sm);
+  }
+  edges = b200::warp_sum(edges);
+  if (b200::lane_id() == 0 && edges) atomicAdd(counts + 1, edges);
+  if (threadIdx.x == 0 && fetched) atomicAdd(counts + 4, fetched * 4096);  // bytes pulled over NVLink
+}
+
 }  // namespace
 
 struct ess_dist_s {
@@ -650,11 +730,18 @@ struct ess_dist_s {
   bool peer_ready = false;
   std::size_t inbox_off = 0, gather_off[2] = {0, 0}, flag_off[2] = {0, 0};
   unsigned epoch = 0;
+  // SSSP over peer memory: replica + dirty words in one IPC-mapped allocation per rank
+  float* replica_window = nullptr;
+  replicas_t replicas{};
+  bool sssp_peer_tried = false, sssp_peer_ready = false;
   unsigned* done_counter = nullptr;  // device word of raise_flags_when_grid_done
   unsigned* timed_out = nullptr;     // pinned, mapped
   ~ess_dist_s() {
     for (int p = 0; p < world && p < max_peers; ++p)
       if (p != rank && peers.base[p]) cudaIpcCloseMemHandle(peers.base[p]);
+    for (int p = 0; p < world && p < max_peers; ++p)
+      if (p != rank && replicas.value[p]) cudaIpcCloseMemHandle(const_cast<float*>(replicas.value[p]));
+    if (replica_window) cudaFree(replica_window);
     if (window) cudaFree(window);
     if (done_counter) cudaFree(done_counter);
     if (timed_out) cudaFreeHost(timed_out);
@@ -999,6 +1086,41 @@ static __global__ void sssp_seed_kernel(long long source, long long row_begin, u
   }
 }
 
+/// First peer-memory SSSP on this handle: allocate replica + dirty words, exchange IPC handles, map the peers.
+/// Collective (every rank calls it at the same point); all ranks agree on the outcome.
+static void setup_sssp_window(ess_dist_t d) {
+  d->sssp_peer_tried = true;
+  auto* c = d->ctx->single();
+  auto stream = c->stream();
+  const int world = d->world, rank = d->rank;
+  const std::size_t n = std::size_t(d->n_global), chunks = (n + 1023) / 1024;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  bool ok = cudaMalloc(&d->replica_window, (n + chunks) * sizeof(float)) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine, d->replica_window) == cudaSuccess;
+  memory::device_array_t<unsigned char> handles(std::size_t(world + 1) * sizeof(mine));
+  std::vector<cudaIpcMemHandle_t> all(world);
+  unsigned char* my_slot = handles.data() + std::size_t(world) * sizeof(mine);
+  cudaMemcpyAsync(my_slot, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream);
+  nccl_check(nccl().AllGather(my_slot, handles.data(), sizeof(mine), ncclUint8, d->comm, stream), "allgather ipc handles");
+  cudaMemcpyAsync(all.data(), handles.data(), std::size_t(world) * sizeof(mine), cudaMemcpyDeviceToHost, stream);
+  c->synchronize();
+  for (int p = 0; p < world && ok; ++p) {
+    void* mapped = d->replica_window;
+    if (p != rank) ok = cudaIpcOpenMemHandle(&mapped, all[p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    d->replicas.value[p] = static_cast<const float*>(mapped);
+    d->replicas.dirty[p] = ok ? reinterpret_cast<const unsigned*>(static_cast<const float*>(mapped) + n) : nullptr;
+  }
+  cudaGetLastError();
+  d->counts_host[0] = ok ? 1 : 0;
+  cudaMemcpyAsync(d->counts_dev.data(), d->counts_host, sizeof(long long), cudaMemcpyHostToDevice, stream);
+  nccl_check(nccl().AllReduce(d->counts_dev.data(), d->counts_dev.data(), 1, ncclInt64, ncclMin, d->comm, stream),
+             "allreduce sssp window");
+  cudaMemcpyAsync(d->counts_host, d->counts_dev.data(), sizeof(long long), cudaMemcpyDeviceToHost, stream);
+  c->synchronize();
+  d->sssp_peer_ready = d->counts_host[0] == 1;
+}
+
 int ess_dist_sssp(ess_dist_t d, int64_t source, ess_run_info* info) {
   ESS_TRY
   if (!d) return ess::fail("ess_dist_sssp: null handle");
@@ -1009,9 +1131,15 @@ int ess_dist_sssp(ess_dist_t d, int64_t source, ess_run_info* info) {
   ess_graph_t g = d->graph;
   const int world = d->world, rank = d->rank;
   const std::size_t per = std::size_t(d->per), n = std::size_t(d->n_global);
-  d->replica.resize(n);
+  // exchange: fused peer-memory reduce+collect when the windows could be mapped, else ncclReduceScatter(min)
+  const bool want_peer = d->peer_ready && ess::dist_peer_exchange() != 0 && world > 1 && per % 1024 == 0;
+  if (want_peer && !d->sssp_peer_tried) setup_sssp_window(d);
+  const bool peer = want_peer && d->sssp_peer_ready;
+  if (!peer) d->replica.resize(n);
   d->dist_local.resize(per);
-  float* replica = d->replica.data();
+  float* replica = peer ? d->replica_window : d->replica.data();
+  unsigned* dirty = peer ? reinterpret_cast<unsigned*>(d->replica_window + n) : nullptr;
+  const std::size_t dirty_words = (n + 1023) / 1024;
   float* owned = replica + std::size_t(rank) * per;  // the reduce_scatter lands here (in place)
   float* dist_local = d->dist_local.data();
   int* active = d->fresh_list.data();
@@ -1027,19 +1155,48 @@ int ess_dist_sssp(ess_dist_t d, int64_t source, ess_run_info* info) {
   long long my_count = (source >= d->row_begin && source < d->row_begin + d->per) ? 1 : 0;
   long long total = 1, relaxed = 0, exchanged = 0;
   int rounds = 0;
+  if (peer) cudaMemsetAsync(counts + 4, 0, sizeof(long long), stream);  // bytes this rank pulls over NVLink
   while (total > 0) {
     ++rounds;
-    ESS_WITH_GRAPH(g, G, { partition_relax(d->ctx, G, active, my_count, dist_local, replica); })
-    nccl_check(api.ReduceScatter(replica, owned, per, ncclFloat, ncclMin, d->comm, stream), "reduce_scatter");
-    exchanged += (long long)(world - 1) * (long long)per * 4;
-    cudaMemsetAsync(counts, 0, 2 * sizeof(long long), stream);
-    ESS_WITH_GRAPH(g, G, { partition_collect(d->ctx, G, owned, dist_local, active, reinterpret_cast<int64_t*>(counts)); })
+    if (peer) {
+      const unsigned epoch = ++d->epoch;
+      cudaMemsetAsync(dirty, 0, dirty_words * sizeof(unsigned), stream);  // peers finished reading: all_reduce below
+      ESS_WITH_GRAPH(g, G, { partition_relax(d->ctx, G, active, my_count, dist_local, replica, dirty); })
+      peer_signal_kernel<<<1, 32, 0, stream>>>(d->peers, world, rank, d->flag_off[0], epoch);
+      peer_wait_kernel<<<1, 32, 0, stream>>>(d->window + d->flag_off[0], world, epoch, d->timed_out);
+      cudaMemsetAsync(counts, 0, 2 * sizeof(long long), stream);
+      const unsigned grid = gcuda::persistent_grid(*c, per / 1024, 8);
+      auto* cnt = reinterpret_cast<b200::counter_t*>(counts);
+      if (g->offset_bits == 64)
+        sssp_peer_reduce_collect_kernel<int64_t><<<grid, 256, 0, stream>>>(
+            g->g64.get_row_offsets(), unsigned(per), d->row_begin, d->replicas, world, rank, replica, dist_local, active, cnt);
+      else
+        sssp_peer_reduce_collect_kernel<int32_t><<<grid, 256, 0, stream>>>(
+            g->g32.get_row_offsets(), unsigned(per), d->row_begin, d->replicas, world, rank, replica, dist_local, active, cnt);
+      c->profiler().launches_total += 3;
+    } else {
+      ESS_WITH_GRAPH(g, G, { partition_relax(d->ctx, G, active, my_count, dist_local, replica); })
+      nccl_check(api.ReduceScatter(replica, owned, per, ncclFloat, ncclMin, d->comm, stream), "reduce_scatter");
+      exchanged += (long long)(world - 1) * (long long)per * 4;
+      cudaMemsetAsync(counts, 0, 2 * sizeof(long long), stream);
+      ESS_WITH_GRAPH(g, G, { partition_collect(d->ctx, G, owned, dist_local, active, reinterpret_cast<int64_t*>(counts)); })
+    }
     nccl_check(api.AllReduce(counts, counts + 2, 2, ncclInt64, ncclSum, d->comm, stream), "allreduce counts");
     cudaMemcpyAsync(d->counts_host, counts, 4 * sizeof(long long), cudaMemcpyDeviceToHost, stream);
     error::throw_if_exception(cudaStreamSynchronize(stream), "dist sssp round");  // the one host sync of the round
+    if (peer && *d->timed_out) {
+      const unsigned who = *d->timed_out - 1;
+      *d->timed_out = 0;
+      throw error::exception_t("ess_dist_sssp: peer " + std::to_string(who) + " did not finish its relaxation round");
+    }
     my_count = d->counts_host[0];
     total = d->counts_host[2];
     relaxed += d->counts_host[3];
+  }
+  if (peer) {
+    cudaMemcpyAsync(d->counts_host, counts + 4, sizeof(long long), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    exchanged = d->counts_host[0];
   }
   cudaEventRecord(t1, stream);
   cudaEventSynchronize(t1);
@@ -1051,6 +1208,7 @@ int ess_dist_sssp(ess_dist_t d, int64_t source, ess_run_info* info) {
   if (info) {
     info->reserved[0] = exchanged;
     info->reserved[1] = relaxed;
+    info->reserved[2] = peer ? 1 : 0;
   }
   return 0;
   ESS_CATCH

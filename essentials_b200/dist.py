@@ -379,7 +379,8 @@ class NativePartitionedBFS:
         info = ess.RunInfo()
         ess._check(ess.lib().ess_dist_sssp(self.handle, int(source), byref(info)), "ess_dist_sssp")
         return {"iterations": int(info.iterations), "nvlink_bytes_received": int(info.reserved[0]),
-                "relaxed_edges": int(info.reserved[1]), "enact_ms": float(info.enact_ms)}
+                "relaxed_edges": int(info.reserved[1]), "enact_ms": float(info.enact_ms),
+                "exchange": "peer-memory" if int(info.reserved[2]) else "nccl"}
 
     def _fetch_dist(self):
         if getattr(self, "dist_local", None) is None:

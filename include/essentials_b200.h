@@ -245,9 +245,13 @@ ESS_API int ess_dist_copy_depth(ess_dist_t d, int32_t* d_out); /* owned depth sl
  *                              ncclReduceScatter in place, or torch.distributed)
  *   ess_sssp_partition_collect rows with reduced[v] < dist_local[v] adopt it and are appended to d_active_list;
  *                              d_counts[0] += rows, d_counts[1] += their out-degrees (two int64 the caller zeroes).
- * ess_dist_sssp runs the whole loop natively with NCCL; info->iterations = rounds, reserved[0] = bytes received
- * per rank, reserved[1] = edges relaxed (all ranks). Distances of the owned rows: ess_dist_copy_dist
- * (FLT_MAX = unreachable). */
+ * ess_dist_sssp runs the whole loop natively. When the peers' windows are mapped (ess_dist_exchange_kind == 1 and
+ * n_global/world a multiple of 1024) exchange and filter are ONE kernel over peer memory: relax also raises a dirty
+ * word per 1024-entry chunk it lowered, and each owner fetches only the dirty chunks of its rows from the peers'
+ * replicas (float4 loads over NVLink), takes the minimum and collects what improved; otherwise
+ * ncclReduceScatter(min) + ess_sssp_partition_collect. info->iterations = rounds, reserved[0] = bytes received by
+ * this rank, reserved[1] = edges relaxed (all ranks), reserved[2] = 1 if the peer-memory path ran. Distances of the
+ * owned rows: ess_dist_copy_dist (FLT_MAX = unreachable). */
 ESS_API int ess_sssp_partition_relax(ess_context_t ctx, ess_graph_t g, const int32_t* d_active_list,
                                      int64_t active_count, const float* d_dist_local, float* d_replica);
 ESS_API int ess_sssp_partition_collect(ess_context_t ctx, ess_graph_t g, const float* d_reduced, float* d_dist_local,

@@ -61,7 +61,8 @@ def check_sssp():
         n_r, m_r = solver.reached_work() if args.python_loop else solver.reached_work_sssp()
         line = (f"src={s} rounds={info['iterations']} wall={ms:.2f} ms device={info['enact_ms']:.2f} ms "
                 f"reached={n_r} m'={m_r} relaxed={info['relaxed_edges']} "
-                f"GTEPS={m_r / max(ms, 1e-9) / 1e6:.2f} recvMB={info['nvlink_bytes_received'] / 1e6:.1f}")
+                f"GTEPS={m_r / max(ms, 1e-9) / 1e6:.2f} recvMB={info['nvlink_bytes_received'] / 1e6:.1f} "
+                f"exchange={info.get('exchange', 'torch.distributed')}")
         if not args.no_check:
             got = solver.gather_dist()
             if rank == 0:
@@ -129,6 +130,20 @@ if "bfs" in algs:
                       " ".join(f"{t:.3f}" for t in times) + f"  mean={sum(times) / len(times):.3f}", flush=True)
 if "sssp" in algs:
     check_sssp()
+    if args.compare_exchange and not args.python_loop:
+        for mode in (1, 0, 1, 0):
+            ess.tune("dist_peer_exchange", mode)
+            times, kinds = [], set()
+            for s in srcs:
+                dist.barrier()
+                torch.cuda.synchronize()
+                info = runner.sssp(s)
+                times.append(info["enact_ms"])
+                kinds.add(info["exchange"])
+            if rank == 0:
+                print(f"sssp exchange={'/'.join(sorted(kinds)):11s} device ms per source: " +
+                      " ".join(f"{t:.3f}" for t in times) + f"  mean={sum(times) / len(times):.3f}", flush=True)
+        ess.tune("dist_peer_exchange", 1)
 flag = torch.tensor([int(ok)], device=dev)
 dist.broadcast(flag, 0)
 dist.destroy_process_group()

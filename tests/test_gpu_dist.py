@@ -27,13 +27,16 @@ def test_partitioned_bfs_two_gpus(loop):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (CPU gloo test covers the host logic)")
-@pytest.mark.parametrize("loop", ["native", "python"])
+@pytest.mark.parametrize("loop", ["native", "native-nccl", "python"])
 def test_partitioned_sssp_two_gpus(loop):
-    """ess_dist_sssp (C++ + ncclReduceScatter(min)) and PartitionedSSSP (torch.distributed) against the single-GPU
-    ess_sssp distances, bit for bit."""
+    """ess_dist_sssp with the fused peer-memory reduce+collect, the same loop over ncclReduceScatter(min), and
+    PartitionedSSSP (torch.distributed) against the single-GPU ess_sssp distances, bit for bit."""
+    port = {"native": "29519", "native-nccl": "29521", "python": "29520"}[loop]
+    extra = {"native": [], "native-nccl": ["--nccl-exchange"], "python": ["--python-loop"]}[loop]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29519" if loop == "native" else "29520",
-           os.path.join(ROOT, "scripts", "dist_check.py"), "--scale", "17", "--alg", "sssp"] + \
-          (["--python-loop"] if loop == "python" else [])
+           "127.0.0.1", "--master-port", port, os.path.join(ROOT, "scripts", "dist_check.py"), "--scale", "17", "--alg",
+           "sssp"] + extra
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DIST_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    if loop.startswith("native"):
+        assert ("exchange=nccl" if loop == "native-nccl" else "exchange=peer-memory") in out.stdout, out.stdout[-2000:]
