@@ -52,6 +52,7 @@ std::enable_if_t<type == parallel_for_each_t::element> execute(frontier_t& f, fu
   kernels::for_each_element_kernel<type_t>
       <<<gcuda::persistent_grid(*ctx, (count + 255) / 256, 8), 256, 0, ctx->stream()>>>(f.data(), count, op);
   error::check_last("parallel_for element");
+  ctx->synchronize();  // as the reference (blocking thrust::cuda::par, for.hxx:33-41): callers read results on return
 }
 
 /// vertex / edge / weight: every vertex id, edge id or edge weight of the graph.
@@ -70,6 +71,7 @@ std::enable_if_t<type != parallel_for_each_t::element> execute(graph_t& G, func_
   else
     kernels::for_each_index_kernel<index_t><<<grid, 256, 0, ctx->stream()>>>(count, op);
   error::check_last("parallel_for");
+  ctx->synchronize();  // reference for.hxx:70-100 blocks too; mst.hxx:236-244 copies a flag to the host right after
 }
 
 }  // namespace parallel_for

@@ -315,7 +315,8 @@ def ref_on_ours():
 
 
 def ref_on_ours_extra(alg: str, csr, *tensors_and_params):
-    """bc / spmv of the reference's headers on our operators (no all-reference counterpart links: moderngpu)."""
+    """bc / spmv / hits / mst of the reference's headers on our operators (no all-reference counterpart links:
+    moderngpu)."""
     import torch
     n, m, off, col, val = _gpu_args(csr)
     R = ref_on_ours()
@@ -332,6 +333,16 @@ def ref_on_ours_extra(alg: str, csr, *tensors_and_params):
         R.refours_spmv.restype = c_float
         R.refours_spmv.argtypes = _G + [c_void_p, c_void_p]
         ms = R.refours_spmv(n, m, off, col, val, c_void_p(x.data_ptr()), c_void_p(out.data_ptr()))
+    elif alg == "hits":
+        out = torch.zeros(1, dtype=torch.float32, device=dev)
+        R.refours_hits.restype = c_float
+        R.refours_hits.argtypes = _G + [c_int]
+        ms = R.refours_hits(n, m, off, col, val, int(tensors_and_params[0]))
+    elif alg == "mst":
+        out = torch.zeros(1, dtype=torch.float32, device=dev)
+        R.refours_mst.restype = c_float
+        R.refours_mst.argtypes = _G + [c_void_p]
+        ms = R.refours_mst(n, m, off, col, val, c_void_p(out.data_ptr()))
     else:
         raise ValueError(alg)
     torch.cuda.synchronize()

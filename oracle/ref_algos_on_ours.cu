@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY — API-compatibility proof for the drop-in header tree.
 //
-// The REFERENCE's own, UNMODIFIED algorithm headers (include/gunrock/algorithms/{bfs,sssp,pr,ppr,kcore,color}.hxx,
+// The REFERENCE's own, UNMODIFIED algorithm headers (include/gunrock/algorithms/{bfs,sssp,pr,ppr,kcore,color,bc,spmv,
+// hits,mst}.hxx,
 // included by absolute path from /root/reference) are compiled against THIS repository's include/gunrock tree:
 // every `#include <gunrock/...>` inside them resolves to our headers, so their enactors run on our operators,
 // frontier, graph views, context and atomics. Built by `make -C oracle refonours` into
@@ -20,6 +21,8 @@
 #include REF_ALG(color.hxx)
 #include REF_ALG(bc.hxx)    // explicit-buffers merge_path advance, per-depth frontier array (bc.hxx:98-190)
 #include REF_ALG(spmv.hxx)  // neighborreduce (spmv.hxx:107-127)
+#include REF_ALG(hits.hxx)  // advance<block_mapped, forward, graph -> vertices> with non-const lambda refs (hits.hxx:244-264)
+#include REF_ALG(mst.hxx)   // edge frontier, filter<remove> explicit form, parallel_for element/vertex (mst.hxx:226-248)
 
 using namespace gunrock;
 using namespace memory;
@@ -62,5 +65,15 @@ float refours_bc(int n, int m, int* d_off, int* d_col, float* d_val, int src, fl
 }
 float refours_spmv(int n, int m, int* d_off, int* d_col, float* d_val, float* d_x, float* d_y) {
   REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); return gunrock::spmv::run(G, d_x, d_y);)
+}
+// hits::run as the reference's driver calls it (examples/algorithms/hits/hits.cu:40-43). With the reference's own
+// problem_t the scores start at zero, so is_converged() holds before the first iteration (hits.hxx:168-176): the
+// call proves the header instantiates and links against our operators, nothing more.
+float refours_hits(int n, int m, int* d_off, int* d_col, float* d_val, int max_iterations) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); gunrock::hits::param_c param{max_iterations};
+            gunrock::hits::result_c result{G}; return gunrock::hits::run(G, param, result);)
+}
+float refours_mst(int n, int m, int* d_off, int* d_col, float* d_val, float* d_weight) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); return gunrock::mst::run(G, d_weight);)
 }
 }  // extern "C"

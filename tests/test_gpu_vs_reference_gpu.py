@@ -146,3 +146,39 @@ def test_reference_bc_and_spmv_headers_on_our_operators(ctx):
     want = torch.zeros(weighted.n, device="cuda", dtype=torch.float64).index_add_(
         0, rows, (weighted.values.double() * x[weighted.indices.long()].double()))
     assert torch.allclose(y.double(), want, rtol=1e-5, atol=1e-5)
+
+
+_MST_SNIPPET = """
+import sys, numpy as np, torch, scipy.sparse as sp
+from scipy.sparse.csgraph import minimum_spanning_tree
+sys.path.insert(0, {root!r})
+import oracle
+from essentials_b200 import graphgen as gg
+grid = gg.grid_csr(24, 17, device="cuda")
+off, col, val = grid.host()
+assert np.unique(val).size == grid.m // 2, "distinct weights keep Boruvka free of ties"
+got, ms = oracle.ref_on_ours_extra("mst", grid)
+want = minimum_spanning_tree(sp.csr_matrix((val.astype(np.float64), col, off), shape=(grid.n, grid.n))).sum()
+print("MST", float(got.item()), float(want))
+_, hits_ms = oracle.ref_on_ours_extra("hits", grid, 20)
+print("HITS", hits_ms)
+"""
+
+
+@needs_compat
+def test_reference_hits_and_mst_headers_on_our_operators():
+    """§8f row 4: mst.hxx (edge frontier, filter<remove> explicit form, parallel_for over elements and vertices,
+    get_source_vertex) and hits.hxx (advance<block_mapped, graph -> vertices>) of the reference, unmodified, on our
+    operators. MST weight against scipy's Kruskal. Runs in a child process with a timeout: the reference's pointer
+    jumping spins on the device if a root cycle ever formed, and that must not be able to hang the suite."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", _MST_SNIPPET.format(root=root)], capture_output=True, text=True,
+                         timeout=120)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("MST")][0].split()
+    got, want = float(line[1]), float(line[2])
+    assert abs(got - want) <= 1e-4 * want, (got, want)
+    assert any(l.startswith("HITS") for l in out.stdout.splitlines())
