@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY — API-compatibility proof for the drop-in header tree.
 //
 // The REFERENCE's own, UNMODIFIED algorithm headers (include/gunrock/algorithms/{bfs,sssp,pr,ppr,kcore,color,bc,spmv,
-// hits,mst}.hxx,
+// hits,mst,geo,spgemm}.hxx,
 // included by absolute path from /root/reference) are compiled against THIS repository's include/gunrock tree:
 // every `#include <gunrock/...>` inside them resolves to our headers, so their enactors run on our operators,
 // frontier, graph views, context and atomics. Built by `make -C oracle refonours` into
@@ -23,6 +23,8 @@
 #include REF_ALG(spmv.hxx)  // neighborreduce (spmv.hxx:107-127)
 #include REF_ALG(hits.hxx)  // advance<block_mapped, forward, graph -> vertices> with non-const lambda refs (hits.hxx:244-264)
 #include REF_ALG(mst.hxx)   // edge frontier, filter<remove> explicit form, parallel_for element/vertex (mst.hxx:226-248)
+#include REF_ALG(geo.hxx)     // instantiated only (parallel_for + advance clients; no checker for its heuristic output)
+#include REF_ALG(spgemm.hxx)  // instantiated only (advance<block_mapped, graph -> none>, parallel_for::vertex)
 
 using namespace gunrock;
 using namespace memory;
@@ -75,5 +77,21 @@ float refours_hits(int n, int m, int* d_off, int* d_col, float* d_val, int max_i
 }
 float refours_mst(int n, int m, int* d_off, int* d_col, float* d_val, float* d_weight) {
   REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); return gunrock::mst::run(G, d_weight);)
+}
+// Instantiation-only proofs: these two link against our operators but have no independent checker here (geo is a
+// heuristic, spgemm leaves an upper-bound layout in C), so the tests do not call them.
+struct csr_standin_t {  // the members spgemm.hxx touches of format::csr_t (formats/csr.hxx:30-60)
+  int number_of_rows = 0, number_of_columns = 0, number_of_nonzeros = 0;
+  thrust::device_vector<int> row_offsets, column_indices;
+  thrust::device_vector<float> nonzero_values;
+};
+float refours_geo(int n, int m, int* d_off, int* d_col, float* d_val, void* d_coordinates, unsigned iterations) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val);
+            return gunrock::geo::run(G, static_cast<gunrock::geo::coordinates_t*>(d_coordinates), iterations, 10u);)
+}
+float refours_spgemm(int n, int m, int* d_off, int* d_col, float* d_val, int* nnz_out) {
+  REF_GUARD(auto A = make_graph(n, m, d_off, d_col, d_val); auto B = make_graph(n, m, d_off, d_col, d_val);
+            csr_standin_t C; float ms = gunrock::spgemm::run(A, B, C); if (nnz_out) *nnz_out = C.number_of_nonzeros;
+            return ms;)
 }
 }  // extern "C"
