@@ -193,6 +193,32 @@ def ref_load_mtx(path: str):
     return o, c, v
 
 
+def ref_write_csr_binary(path: str, off, col, val):
+    """The reference's csr_t::write_binary (formats/csr.hxx:203-234) on the given arrays."""
+    off, col, val = _i32(off), _i32(col), _f32(val)
+    R = ref()
+    R.ref_write_csr_binary.restype = c_int
+    R.ref_write_csr_binary.argtypes = [ctypes.c_char_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    R.ref_write_csr_binary(path.encode(), off.size - 1, col.size, _ptr(off), _ptr(col), _ptr(val))
+
+
+def ref_read_csr_binary(path: str):
+    """The reference's csr_t::read_binary (formats/csr.hxx:159-201)."""
+    R = ref()
+    n, m = c_int(), c_int()
+    off, col = ctypes.POINTER(c_int)(), ctypes.POINTER(c_int)()
+    val = ctypes.POINTER(c_float)()
+    R.ref_read_csr_binary.restype = c_int
+    R.ref_read_csr_binary(path.encode(), ctypes.byref(n), ctypes.byref(m), ctypes.byref(off), ctypes.byref(col),
+                          ctypes.byref(val))
+    o = np.ctypeslib.as_array(off, (n.value + 1,)).copy()
+    c = np.ctypeslib.as_array(col, (m.value,)).copy() if m.value else np.zeros(0, np.int32)
+    v = np.ctypeslib.as_array(val, (m.value,)).copy() if m.value else np.zeros(0, np.float32)
+    for p in (off, col, val):
+        R.ref_free(ctypes.cast(p, c_void_p))
+    return o, c, v
+
+
 def _ref_csr(off, col):
     off, col = _i32(off), _i32(col)
     return off, col, off.size - 1, col.size

@@ -9,6 +9,7 @@
 //   examples/algorithms/color/color_cpu.hxx:16-72  -> ref_color (Gauss-Seidel; validity reference only)
 //   include/gunrock/algorithms/generate/random.hxx:20-33 -> ref_randoms
 //   include/gunrock/io/matrix_market.hxx:99-240 + formats/csr.hxx:79-157 -> ref_load_mtx
+//   include/gunrock/formats/csr.hxx:159-236 (read_binary / write_binary) -> ref_read_csr_binary / ref_write_csr_binary
 // Built by oracle/Makefile into oracle/_ref/libref_cpu.so with Thrust's CPP (host) backend, so that
 // `memory_space_t::device` vectors are plain host memory and no GPU is needed.
 // Used (a) to pin oracle/oracle.cpp against the reference, (b) to generate tests/golden/*, and
@@ -100,6 +101,29 @@ float ref_ppr(int n, int m, const int* off, const int* col, int n_seeds, float* 
 float ref_color(int n, int m, const int* off, const int* col, int* colors) {
   auto csr = make_csr(n, m, off, col, nullptr);
   return color_cpu::run<ref_csr_t, vertex_t, edge_t, weight_t>(csr, colors);
+}
+
+// The reference's `.csr` binary reader / writer (pins essentials_b200/io.py). Arrays from the reader are
+// malloc'ed; free with ref_free.
+int ref_write_csr_binary(const char* path, int n, int m, const int* off, const int* col, const float* val) {
+  auto csr = make_csr(n, m, off, col, val);
+  csr.write_binary(path);
+  return 0;
+}
+int ref_read_csr_binary(const char* path, int* n, int* m, int** off, int** col, float** val) {
+  ref_csr_t csr;
+  csr.read_binary(path);
+  *n = csr.number_of_rows;
+  *m = csr.number_of_nonzeros;
+  *off = (int*)malloc(sizeof(int) * (*n + 1));
+  *col = (int*)malloc(sizeof(int) * (*m));
+  *val = (float*)malloc(sizeof(float) * (*m));
+  for (int i = 0; i <= *n; ++i) (*off)[i] = csr.row_offsets[i];
+  for (int e = 0; e < *m; ++e) {
+    (*col)[e] = csr.column_indices[e];
+    (*val)[e] = csr.nonzero_values[e];
+  }
+  return 0;
 }
 
 // The reference's seed-free per-index random stream (color.hxx:65 calls it with (0, n)).
