@@ -72,6 +72,8 @@ _SIGNATURES = {
     "ess_randoms": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float]),
     "ess_advance_probe": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64,
                                   POINTER(c_int64), c_void_p, c_int32]),
+    "ess_advance_unique_probe": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64,
+                                  POINTER(c_int64), c_void_p, c_int32]),
     "ess_filter_probe": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, POINTER(c_int64), c_void_p,
                                  c_int32]),
     "ess_uniquify_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_int64)]),
@@ -341,6 +343,21 @@ def advance_probe(ctx: Context, g: Graph, frontier, lb: str = "merge_path", dire
     _check(lib().ess_advance_probe(ctx.handle, g.handle, LOAD_BALANCE[lb], DIRECTION[direction], _p(frontier),
                                    int(frontier.numel()), _p(out), cap, byref(n_out), _p(calls), modulus),
            "ess_advance_probe")
+    return out[: n_out.value], calls
+
+
+def advance_unique_probe(ctx: Context, g: Graph, frontier, lb: str = "merge_path", modulus: int = 3):
+    """operators::advance::execute_unique (fused advance + uniquify) with the fixed test operator, run twice on the
+    same bitmap. Returns (duplicate-free kept neighbours, per-edge call counts == 2 on every expanded edge)."""
+    import torch
+    _need_cuda(frontier)
+    calls = torch.zeros(max(g.m, 1), dtype=torch.int32, device=frontier.device)
+    n_out = c_int64(0)
+    cap = int(g.m) + 1
+    out = torch.empty(cap, dtype=torch.int32, device=frontier.device)
+    _check(lib().ess_advance_unique_probe(ctx.handle, g.handle, LOAD_BALANCE[lb], _p(frontier), int(frontier.numel()),
+                                          _p(out), cap, byref(n_out), _p(calls), modulus),
+           "ess_advance_unique_probe")
     return out[: n_out.value], calls
 
 

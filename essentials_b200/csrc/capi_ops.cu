@@ -41,6 +41,37 @@ int advance_probe(ess_context_t ctx, graph_t& G, int direction, const int32_t* d
   return 0;
 }
 
+/// As advance_probe through operators::advance::execute_unique (fused advance + uniquify).
+template <operators::load_balance_t lb, typename graph_t>
+int advance_unique_probe(ess_context_t ctx, graph_t& G, const int32_t* d_frontier, int64_t frontier_size,
+                         int32_t* d_out, int64_t out_capacity, int64_t* out_count, int32_t* d_edge_calls,
+                         int32_t modulus) {
+  using edge_t = typename graph_t::edge_type;
+  borrowed_frontier_t<edge_t> in, out;
+  in.ptr = const_cast<int32_t*>(d_frontier);
+  in.count = in.cap = std::size_t(frontier_size);
+  out.ptr = d_out;
+  out.cap = d_out ? std::size_t(out_capacity) : 0;
+  memory::device_array_t<edge_t> segments;
+  frontier::frontier_t<int32_t, edge_t, frontier::frontier_kind_t::vertex_frontier, frontier::frontier_view_t::bitmap> seen;
+  auto op = [d_edge_calls, modulus] __host__ __device__(int32_t const& src, int32_t const& nbr, edge_t const& e,
+                                                        float const& w) -> bool {
+    if (d_edge_calls) math::atomic::add(d_edge_calls + e, 1);
+    return (long long)(src + nbr + (long long)e) % modulus != 0;
+  };
+  using namespace operators;
+  // twice: the second pass must see an all-clear map again and reproduce the first one's set
+  for (int pass = 0; pass < 2; ++pass)
+    advance::execute_unique<lb, advance_direction_t::forward, advance_io_type_t::vertices>(G, op, &in, &out, segments,
+                                                                                          seen, *ctx->ctx);
+  if (out_count) *out_count = int64_t(out.count);
+  if (d_out && out.ptr != d_out) {
+    std::size_t fit = out.count < std::size_t(out_capacity) ? out.count : std::size_t(out_capacity);
+    cudaMemcpy(d_out, out.ptr, fit * sizeof(int32_t), cudaMemcpyDeviceToDevice);
+  }
+  return 0;
+}
+
 template <operators::filter_algorithm_t alg, typename graph_t>
 int filter_probe(ess_context_t ctx, graph_t& G, const int32_t* d_in, int64_t size, int32_t* d_out, int64_t* out_count,
                  int32_t* d_calls, int32_t modulus) {
@@ -77,6 +108,22 @@ int ess_advance_probe(ess_context_t ctx, ess_graph_t g, int lb, int direction, c
     ESS_WITH_GRAPH(g, G, {
       return advance_probe<LB>(ctx, G, direction, d_frontier, frontier_size, d_out, out_capacity, out_count,
                                d_edge_calls, modulus);
+    })
+  });
+  ESS_CATCH
+}
+
+int ess_advance_unique_probe(ess_context_t ctx, ess_graph_t g, int lb, const int32_t* d_frontier, int64_t frontier_size,
+                             int32_t* d_out, int64_t out_capacity, int64_t* out_count, int32_t* d_edge_calls,
+                             int32_t modulus) {
+  ESS_TRY
+  if (!ctx || !g) return ess::fail("ess_advance_unique_probe: null argument");
+  if (modulus <= 0) modulus = 1 << 30;
+  return ess::with_load_balance(lb, [&](auto lbc) -> int {
+    constexpr auto LB = decltype(lbc)::value;
+    ESS_WITH_GRAPH(g, G, {
+      return advance_unique_probe<LB>(ctx, G, d_frontier, frontier_size, d_out, out_capacity, out_count, d_edge_calls,
+                                      modulus);
     })
   });
   ESS_CATCH

@@ -156,6 +156,14 @@ ESS_API int ess_advance_probe(ess_context_t ctx, ess_graph_t g, int lb, int dire
                       int64_t frontier_size, int32_t* d_out, int64_t out_capacity, int64_t* out_count,
                       int32_t* d_edge_calls, int32_t modulus);
 
+/* The same fixed operator through operators::advance::execute_unique — fused advance + uniquify, the step the
+ * reference leaves commented out after its advances (sssp.hxx:146-150, bfs.hxx:128-131): the operator still runs
+ * once per edge (d_edge_calls), but every kept neighbour appears once in d_out. The probe runs the call twice on
+ * the same bitmap (the second pass proves the map was left clear), so d_edge_calls ends at 2 per edge. */
+ESS_API int ess_advance_unique_probe(ess_context_t ctx, ess_graph_t g, int lb, const int32_t* d_frontier,
+                                     int64_t frontier_size, int32_t* d_out, int64_t out_capacity, int64_t* out_count,
+                                     int32_t* d_edge_calls, int32_t modulus);
+
 /* operators::filter::execute<alg>(G, op, in, out, ctx) — include/gunrock/framework/operators/filter/filter.hxx:59-86 —
  * with op(v) := { atomicAdd(&d_calls[v], 1); return v % modulus != 0; }. d_out needs `size` elements
  * (may equal d_in for BYPASS). */

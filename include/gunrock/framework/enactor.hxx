@@ -99,6 +99,8 @@ struct enactor_t {
   int buffer_selector;
   int iteration;
   direction_state_t<vertex_t, edge_t> direction;
+  /// "already emitted in this call" bitmap of operators::advance::execute_unique (all clear between calls).
+  typename direction_state_t<vertex_t, edge_t>::bits_t unique_seen;
 
   enactor_t(const enactor_t&) = delete;
   enactor_t& operator=(const enactor_t&) = delete;

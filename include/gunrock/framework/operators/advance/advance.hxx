@@ -394,6 +394,53 @@ void execute(graph_t& G, enactor_type* E, operator_type op, gcuda::multi_context
   if (swap_buffers && (output_type != advance_io_type_t::none)) E->swap_frontier_buffers();
 }
 
+/**
+ * @brief Fused advance + uniquify (the step the reference leaves commented out after its advances, sssp.hxx:146-150,
+ * bfs.hxx:128-131). Same call as the enactor form of execute<lb, direction, input, vertices>: `op` runs on every
+ * edge exactly once, but each kept neighbour is written to the output frontier ONCE however many edges kept it —
+ * the expansion kernels test-and-set a per-enactor bitmap (n/8 bytes, L2 resident) at emission, and an
+ * O(|output|) epilogue clears the words again. Replaces advance -> uniquify (or the bypass filter SSSP uses to
+ * drop repeats) without the intermediate Σdeg-long frontier.
+ */
+template <load_balance_t lb, advance_direction_t direction, advance_io_type_t input_type, typename graph_t,
+          typename operator_t, typename frontier_t, typename work_tiles_t, typename bitmap_t>
+void execute_unique(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, work_tiles_t& segments,
+                    bitmap_t& seen, gcuda::multi_context_t& context) {
+  static_assert(direction != advance_direction_t::optimized, "execute_unique: forward or backward");
+  static_assert(lb != load_balance_t::warp_mapped && lb != load_balance_t::work_stealing,
+                "execute_unique: thread_mapped, block_mapped, merge_path or bucketing");
+  error::throw_if_exception(context.size() != 1, "`context.size() != 1` not supported");
+  auto* ctx = context.get_context(0);
+  auto stream = ctx->stream();
+  const std::size_t n = std::size_t(G.get_number_of_vertices());
+  if (seen.get_universe() != n) {  // (re)sized maps start all clear
+    seen.resize(n, stream);
+    seen.fill(0, stream);
+  }
+  detail::expand<lb, direction == advance_direction_t::backward, input_type, advance_io_type_t::vertices,
+                 detail::visit_t::unique_output>(G, op, input, output, segments, *ctx, seen.data());
+  const std::size_t count = output->get_number_of_elements();
+  if (count) {
+    ctx->profiler().begin(gcuda::profiler_t::dense_state, stream);
+    kernels::clear_emitted_kernel<<<gcuda::persistent_grid(*ctx, (count + 255) / 256, 8), 256, 0, stream>>>(
+        output->data(), count, seen.data());
+    ctx->profiler().end(stream);
+    ctx->synchronize();  // completion contract: the map is clear and the frontier final on return
+  }
+}
+
+/// Enactor form: E's input frontier -> E's output frontier, E->unique_seen as the bitmap, buffers swapped.
+template <load_balance_t lb = load_balance_t::merge_path,
+          advance_direction_t direction = advance_direction_t::forward,
+          advance_io_type_t input_type = advance_io_type_t::vertices, typename graph_t, typename enactor_type,
+          typename operator_type>
+void execute_unique(graph_t& G, enactor_type* E, operator_type op, gcuda::multi_context_t& context,
+                    bool swap_buffers = true) {
+  execute_unique<lb, direction, input_type>(G, op, E->get_input_frontier(), E->get_output_frontier(),
+                                            E->scanned_work_domain, E->unique_seen, context);
+  if (swap_buffers) E->swap_frontier_buffers();
+}
+
 }  // namespace advance
 }  // namespace operators
 }  // namespace gunrock

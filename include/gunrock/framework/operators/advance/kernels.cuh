@@ -49,8 +49,11 @@ constexpr int prep_items = 4;                         // frontier items per thre
 constexpr long long big_degree = 8192;                // adjacency lists this long are expanded grid-wide
 constexpr int warp_degree = 32;                       // bucketing: lists at least this long get a warp
 
-/// Visited-bitmap handling of an advance: `none` = reference semantics (operator runs on every edge).
-enum class visit_t { none, test_and_set };
+/// Visited-bitmap handling of an advance: `none` = reference semantics (operator runs on every edge);
+/// `test_and_set` = direction-optimised traversal (neighbours already in the bitmap are skipped, survivors join it);
+/// `unique_output` = fused uniquify: the operator still runs on every edge, but a neighbour it keeps is emitted
+/// only by the first edge that sets its bit in the (per-call, initially clear) bitmap.
+enum class visit_t { none, test_and_set, unique_output };
 
 /// `fresh_edges` (test_and_set only) accumulates the out-degree of every vertex this thread adds to the
 /// visited set: Σdeg of the next frontier is Beamer's m_f, needed by the push/pull switch.
@@ -70,7 +73,26 @@ __device__ __forceinline__ bool visit_edge(const graph::adjacency_t<vertex_t, ed
       if (keep) fresh_edges += counter_t(A.offsets[neighbor + 1] - A.offsets[neighbor]);
     }
   }
+  if constexpr (policy == visit_t::unique_output) {
+    if (keep) {
+      const unsigned bit = 1u << (unsigned(neighbor) & 31u);
+      unsigned* word = &visited[unsigned(neighbor) >> 5];
+      keep = !(*word & bit) && !(atomicOr(word, bit) & bit);  // the plain read keeps repeats off the atomic units
+    }
+  }
   return keep;
+}
+
+/// unique_output epilogue: clears the bitmap words of the emitted vertices (only emitted vertices ever set a bit,
+/// so storing zero to their words restores the all-clear state in O(|output|)).
+template <typename vertex_t>
+__global__ void __launch_bounds__(256)
+    clear_emitted_kernel(const vertex_t* __restrict__ output, std::size_t count, unsigned* __restrict__ seen) {
+  for (std::size_t i = std::size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+       i += std::size_t(gridDim.x) * blockDim.x) {
+    const vertex_t v = output[i];
+    if (util::limits::is_valid(v)) seen[unsigned(v) >> 5] = 0u;
+  }
 }
 
 /// End-of-kernel flush of a thread's fresh_edges into counters[aux2] (one atomic per warp).

@@ -296,6 +296,33 @@ def test_advance_operator_multiset(ctx, lb, direction):
         assert np.array_equal(calls.cpu().numpy()[: col.size], want_calls[: col.size]), (lb, direction, label)
 
 
+@pytest.mark.parametrize("lb", LBS)
+def test_advance_unique_operator(ctx, lb):
+    """operators::advance::execute_unique (fused advance + uniquify, SURVEY §8f row 1): op still runs once per
+    (frontier item, edge) — the probe calls it twice, so twice — but the output is the SET of kept neighbours, and
+    the second call on the same bitmap reproduces it (the epilogue left the map clear)."""
+    csr = gg.rmat_csr(11, symmetric=False, device="cuda")
+    g = ess.Graph(csr)
+    off, col, _ = csr.host()
+    rng = np.random.default_rng(6)
+    cases = {
+        "random+holes+dups": np.concatenate([rng.integers(0, csr.n, 700), -np.ones(40, np.int64),
+                                             rng.integers(0, csr.n, 30).repeat(2)]),
+        "all": np.arange(csr.n),
+        "single-hub": np.array([int(np.argmax(np.diff(off)))]),
+        "only-holes": -np.ones(17, np.int64),
+        "empty": np.zeros(0, np.int64),
+    }
+    for label, f in cases.items():
+        f = f.astype(np.int32)
+        rng.shuffle(f)
+        out, calls = ess.advance_unique_probe(ctx, g, torch.from_numpy(f).cuda(), lb=lb, modulus=3)
+        want, want_calls = _expected_advance(off, col, f, 3)
+        got = out.cpu().numpy()
+        assert np.array_equal(np.sort(got), np.unique(want)), (lb, label)
+        assert np.array_equal(calls.cpu().numpy()[: col.size], 2 * want_calls[: col.size]), (lb, label)
+
+
 @pytest.mark.parametrize("alg", ["predicated", "remove", "compact", "bypass"])
 def test_filter_operator(ctx, graphs, alg):
     g = graphs["rmat_s10"]
