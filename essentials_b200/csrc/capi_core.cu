@@ -4,6 +4,7 @@
  */
 #include "capi_common.hxx"
 #include <gunrock/algorithms/generate/random.hxx>
+#include <gunrock/algorithms/sssp.hxx>
 
 namespace ess {
 std::string& last_error() {
@@ -76,6 +77,10 @@ int ess_tune(const char* knob, int value) {
   }
   if (k == "pull_hints") {
     gunrock::operators::advance::kernels::pull_hints_enabled() = value;
+    return 0;
+  }
+  if (k == "sssp_fused_unique") {
+    gunrock::sssp::fused_unique() = value;
     return 0;
   }
   if (k == "dist_trace") {

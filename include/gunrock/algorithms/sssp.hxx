@@ -66,6 +66,14 @@ struct problem_t : gunrock::problem_t<graph_t> {
   }
 };
 
+/// Knob (ess_tune "sssp_fused_unique", default on): the level loop uses operators::advance::execute_unique (fused
+/// advance + uniquify) instead of the reference's advance -> bypass-filter pair (0 selects that pair). Same
+/// distances; 5-15 % faster on Kronecker scale-24 (profiles/r01h_probe_sssp_kron24.log).
+inline int& fused_unique() {
+  static int on = 1;
+  return on;
+}
+
 template <typename problem_t, operators::load_balance_t lb, bool near_far = false>
 struct enactor_t : gunrock::enactor_t<problem_t> {
   using base_t = gunrock::enactor_t<problem_t>;
@@ -118,8 +126,13 @@ struct enactor_t : gunrock::enactor_t<problem_t> {
       visited[vertex] = iteration;
       return true;
     };
-    operators::advance::execute<lb>(G, E, shortest_path, context);
-    operators::filter::execute<operators::filter_algorithm_t::bypass>(G, E, drop_repeats, context);
+    if (fused_unique()) {  // one pass: repeats are dropped at emission, no holes reach the next advance
+      operators::advance::execute_unique<lb>(G, E, shortest_path, context);
+      (void)drop_repeats;
+    } else {
+      operators::advance::execute<lb>(G, E, shortest_path, context);
+      operators::filter::execute<operators::filter_algorithm_t::bypass>(G, E, drop_repeats, context);
+    }
   }
 };
 

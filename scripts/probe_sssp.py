@@ -23,6 +23,7 @@ deg = csr.degrees().long()
 for s in gg.pick_sources(csr, args.sources):
     base = None
     for rep in range(args.repeats):
+        ess.tune("sssp_fused_unique", 0)
         for lb in args.lbs.split(","):
             d, info = ess.sssp(ctx, g, s, lb=lb)
             if base is None:
@@ -30,6 +31,12 @@ for s in gg.pick_sources(csr, args.sources):
                 m_r = int(deg[d != 3.4028234663852886e38].sum())
             assert torch.equal(base, d)
             print(f"src={s} rep={rep} {lb:13s} enact={info['enact_ms']:8.2f} ms iters={info['iterations']} "
+                  f"GTEPS={m_r / info['enact_ms'] / 1e6:.2f}", flush=True)
+        ess.tune("sssp_fused_unique", 1)
+        for lb in args.lbs.split(","):
+            d, info = ess.sssp(ctx, g, s, lb=lb)
+            assert torch.equal(base, d)
+            print(f"src={s} rep={rep} {lb + '+unique':20s} enact={info['enact_ms']:8.2f} ms iters={info['iterations']} "
                   f"GTEPS={m_r / info['enact_ms'] / 1e6:.2f}", flush=True)
         for delta in (float(x) for x in args.deltas.split(",")):
             d, info = ess.sssp_delta(ctx, g, s, delta=delta if delta > 0 else 3e38)

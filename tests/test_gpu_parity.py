@@ -165,6 +165,21 @@ def test_sssp_near_far_larger_graphs(ctx):
         assert info["relaxations"] >= grid.m * 0 + 1
 
 
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("lb", LBS)
+def test_sssp_fused_unique_level_loop(ctx, graphs, golden, lb, fused):
+    """gunrock::sssp with operators::advance::execute_unique (default) and with the reference's advance + bypass
+    filter pair (knob 0): same distances."""
+    ess.tune("sssp_fused_unique", fused)
+    try:
+        for name in ("chesapeake", "rmat_s10", "grid_24x17"):
+            for s in golden[name]["sources"]:
+                dist, info = ess.sssp(ctx, graphs[name], int(s), lb=lb)
+                assert np.array_equal(dist.cpu().numpy(), golden[name][f"sssp_{s}"]), (name, int(s), lb)
+    finally:
+        ess.tune("sssp_fused_unique", 1)
+
+
 @pytest.mark.parametrize("delta", [0.0, 0.5, 7.5, 64.0, 3e38])
 def test_sssp_delta_bit_exact(ctx, graphs, golden, delta):
     """gunrock::sssp::run_delta (dense active set, threshold advancing by delta): reference distances for every
