@@ -1,8 +1,10 @@
 /**
  * @file problem.hxx
  * @brief problem_t: algorithm state bound to a graph view and a context; init()/reset() are the two
- * virtuals an algorithm fills in. Same members and accessors as the reference
- * (include/gunrock/framework/problem.hxx:29-59): get_graph() returns the view BY VALUE.
+ * virtuals an algorithm fills in. Member names and accessors are the reference's
+ * (include/gunrock/framework/problem.hxx:29-59) because algorithm headers reach into them:
+ * `graph_slice`, `context`, get_graph() (the view BY VALUE, so it can be captured into kernels),
+ * get_multi_context(), get_single_context(device).
  */
 #pragma once
 
@@ -14,26 +16,32 @@ namespace gunrock {
 
 template <typename graph_t>
 struct problem_t {
-  using vertex_t = typename graph_t::vertex_type;
-  using edge_t = typename graph_t::edge_type;
+  using graph_type = graph_t;
   using weight_t = typename graph_t::weight_type;
+  using edge_t = typename graph_t::edge_type;
+  using vertex_t = typename graph_t::vertex_type;
+  using context_ptr_t = std::shared_ptr<gcuda::multi_context_t>;
 
-  graph_t graph_slice;
-  std::shared_ptr<gcuda::multi_context_t> context;
+  // a problem owns device state: it is neither copied nor sliced
+  problem_t(const problem_t&) = delete;
+  problem_t& operator=(const problem_t&) = delete;
+  virtual ~problem_t() = default;
 
   problem_t() : graph_slice() {}
-  problem_t(graph_t& G, std::shared_ptr<gcuda::multi_context_t> _context) : graph_slice(G), context(_context) {}
-  virtual ~problem_t() = default;
+  problem_t(graph_t& G, context_ptr_t _context) : graph_slice(G), context(std::move(_context)) {}
+
+  /// Algorithm hooks: allocate once / restore the start state before every enact().
+  virtual void init() = 0;
+  virtual void reset() = 0;
 
   auto get_graph() { return graph_slice; }
   auto get_multi_context() { return context; }
   auto get_single_context(gcuda::device_id_t device = 0) { return context->get_context(device); }
+  /// Stream every kernel of this problem's algorithm is enqueued on.
+  auto stream(gcuda::device_id_t device = 0) { return context->get_context(device)->stream(); }
 
-  virtual void init() = 0;
-  virtual void reset() = 0;
-
-  problem_t(const problem_t&) = delete;
-  problem_t& operator=(const problem_t&) = delete;
+  graph_t graph_slice;
+  context_ptr_t context;
 };
 
 }  // namespace gunrock

@@ -114,62 +114,47 @@ constexpr const type_t& min(const type_t& a, const type_t& b) {
 
 namespace atomic {
 
-// Host fallbacks are single-threaded read-modify-writes that still return the old value.
+namespace detail {
+/// Host stand-in of a device read-modify-write: applies `update(old)` in place and hands back the old value,
+/// which is what every wrapper below must return (user lambdas compare against it). Not thread safe, like the
+/// reference's host branch.
+template <typename type_t, typename update_t>
+__host__ __device__ __forceinline__ type_t host_rmw(type_t* address, update_t update) {
+  const type_t before = *address;
+  *address = update(before);
+  return before;
+}
+}  // namespace detail
+
+#ifdef __CUDA_ARCH__
+#define GUNROCK_RMW(device_expr, host_update) return device_expr
+#else
+#define GUNROCK_RMW(device_expr, host_update) \
+  return detail::host_rmw(address, [&](type_t const& before) -> type_t { return host_update; })
+#endif
+
 template <typename type_t>
 __host__ __device__ __forceinline__ type_t add(type_t* address, type_t value) {
-#ifdef __CUDA_ARCH__
-  return atomicAdd(address, value);
-#else
-  type_t old = *address;
-  *address = old + value;
-  return old;
-#endif
+  GUNROCK_RMW(atomicAdd(address, value), before + value);
 }
-
 template <typename type_t>
 __host__ __device__ __forceinline__ type_t min(type_t* address, type_t value) {
-#ifdef __CUDA_ARCH__
-  return gcuda::atomicMin(address, value);
-#else
-  type_t old = *address;
-  *address = std::min<type_t>(old, value);
-  return old;
-#endif
+  GUNROCK_RMW(gcuda::atomicMin(address, value), value < before ? value : before);
 }
-
 template <typename type_t>
 __host__ __device__ __forceinline__ type_t max(type_t* address, type_t value) {
-#ifdef __CUDA_ARCH__
-  return gcuda::atomicMax(address, value);
-#else
-  type_t old = *address;
-  *address = std::max<type_t>(old, value);
-  return old;
-#endif
+  GUNROCK_RMW(gcuda::atomicMax(address, value), before < value ? value : before);
 }
-
 template <typename type_t>
 __host__ __device__ __forceinline__ type_t cas(type_t* address, type_t compare, type_t value) {
-#ifdef __CUDA_ARCH__
-  return atomicCAS(address, compare, value);
-#else
-  type_t old = *address;
-  if (old == compare)
-    *address = value;
-  return old;
-#endif
+  GUNROCK_RMW(atomicCAS(address, compare, value), before == compare ? value : before);
 }
-
 template <typename type_t>
 __host__ __device__ __forceinline__ type_t exch(type_t* address, type_t value) {
-#ifdef __CUDA_ARCH__
-  return atomicExch(address, value);
-#else
-  type_t old = *address;
-  *address = value;
-  return old;
-#endif
+  GUNROCK_RMW(atomicExch(address, value), value);
 }
+
+#undef GUNROCK_RMW
 
 }  // namespace atomic
 }  // namespace math
