@@ -131,7 +131,7 @@ def _sssp_worker(rank, world, port, scale, sources, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_partitioned_sssp_matches_oracle(world):
     scale = 9
     full = gg.rmat_csr(scale, weights="hash")
