@@ -293,6 +293,7 @@ def run_b200(args, rank, world, local_rank):
         out["roofline"] = {
             "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
             "frac": achieved / peak_gbs, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+            "frac_of_nominal_8000_gbs": achieved / 8000.0,
             "launches": d_launches, "avg_launch_ms": d_ms / max(d_launches, 1),
             "algorithmic_bytes_per_launch": bytes_by_class[dom] / max(d_launches, 1),
             "kernel_ms_per_step": {k: v / K for k, v in kernel_ms.items() if v},
