@@ -93,3 +93,34 @@ def test_empty_and_degenerate_inputs():
     assert np.array_equal(oracle.bfs(off, col, 0), [0, 1])
     d = oracle.sssp(off, col, np.array([1, 5, 2, 1], np.float32), 0)
     assert np.array_equal(d, np.array([0, 2], np.float32))
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_matches_reference_code_on_arbitrary_small_graphs():
+    """Property test (hypothesis): arbitrary small directed multigraphs — self loops, parallel edges, isolated and
+    unreachable vertices, equal and zero weights — through the restatement and through the reference's own CPU code."""
+    from hypothesis import given, settings, strategies as st
+
+    @st.composite
+    def graphs(draw):
+        n = draw(st.integers(1, 24))
+        m = draw(st.integers(0, 80))
+        src = draw(st.lists(st.integers(0, n - 1), min_size=m, max_size=m))
+        dst = draw(st.lists(st.integers(0, n - 1), min_size=m, max_size=m))
+        # dyadic weights (exact in float32) incl. zero and repeats: ties and zero-length edges are the hard cases
+        w = draw(st.lists(st.sampled_from([0.0, 0.5, 1.0, 1.0, 2.25, 7.0, 63.984375]), min_size=m, max_size=m))
+        order = np.lexsort((np.array(dst, np.int64), np.array(src, np.int64))) if m else np.zeros(0, np.int64)
+        s = np.array(src, np.int64)[order]
+        off = np.zeros(n + 1, np.int64)
+        np.add.at(off, s + 1, 1)
+        off = np.cumsum(off)
+        return off, np.array(dst, np.int32)[order], np.array(w, np.float32)[order], draw(st.integers(0, n - 1))
+
+    @settings(max_examples=150, deadline=None)
+    @given(graphs())
+    def check(g):
+        off, col, val, s = g
+        assert np.array_equal(oracle.bfs(off, col, s), oracle.ref_bfs(off, col, s))
+        assert np.array_equal(oracle.sssp(off, col, val, s), oracle.ref_sssp(off, col, val, s))
+
+    check()
