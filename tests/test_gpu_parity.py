@@ -209,6 +209,48 @@ def test_sssp_delta_larger_graph_and_work(ctx):
     assert d[iso] == 0 and (np.delete(d, iso) == np.float32(3.4028234663852886e38)).all() and info["rounds"] == 1
 
 
+def _arbitrary_multigraph(rng):
+    """Small directed multigraph with self loops, parallel edges, isolated vertices, zero and tied weights."""
+    n = int(rng.integers(2, 70))
+    m = int(rng.integers(1, 400))
+    src, dst = rng.integers(0, n, m), rng.integers(0, n, m)
+    w = rng.choice(np.array([0.0, 0.5, 1.0, 1.0, 2.25, 7.0, 63.984375], np.float32), m)
+    order = np.lexsort((dst, src))
+    off = np.zeros(n + 1, np.int64)
+    np.add.at(off, src + 1, 1)
+    off = np.cumsum(off).astype(np.int32)
+    return gg.CSR(n, m, torch.from_numpy(off).cuda(), torch.from_numpy(dst[order].astype(np.int32)).cuda(),
+                  torch.from_numpy(w[order]).cuda(), "arbitrary", False)
+
+
+def test_traversals_on_arbitrary_directed_multigraphs(ctx):
+    """The degenerate inputs the oracle property test feeds the reference's CPU code, through every CUDA traversal:
+    forward BFS with each balancer, push/pull BFS over CSR + transposed CSC, SSSP as frontier recipe (fused and
+    reference pair), dense delta and near-far — all bit-equal to the oracle."""
+    rng = np.random.default_rng(77)
+    for trial in range(40):
+        csr = _arbitrary_multigraph(rng)
+        off, col, val = csr.host()
+        g = ess.Graph(csr, csc=ess.transpose(csr))
+        for s in {0, int(rng.integers(0, csr.n))}:
+            want_bfs, want_sssp = oracle.bfs(off, col, s), oracle.sssp(off, col, val, s)
+            for lb in LBS:
+                d, _ = ess.bfs(ctx, g, s, lb=lb)
+                assert np.array_equal(d.cpu().numpy(), want_bfs), (trial, s, lb)
+            d, _ = ess.bfs(ctx, g, s, lb="merge_path", direction="optimized")
+            assert np.array_equal(d.cpu().numpy(), want_bfs), (trial, s, "optimized")
+            for fused in (1, 0):
+                ess.tune("sssp_fused_unique", fused)
+                d, _ = ess.sssp(ctx, g, s, lb="merge_path")
+                assert np.array_equal(d.cpu().numpy(), want_sssp), (trial, s, "frontier", fused)
+            ess.tune("sssp_fused_unique", 1)
+            for delta in (0.0, 1.0, 3e38):
+                d, _ = ess.sssp_delta(ctx, g, s, delta=delta)
+                assert np.array_equal(d.cpu().numpy(), want_sssp), (trial, s, "delta", delta)
+            d, _ = ess.sssp_near_far(ctx, g, s, delta=1.5)
+            assert np.array_equal(d.cpu().numpy(), want_sssp), (trial, s, "near_far")
+
+
 # ------------------------------------------------------------------------------------------------ PageRank
 @pytest.mark.parametrize("mode", ["pull", "block_mapped", "merge_path", "bucketing", "thread_mapped"])
 def test_pagerank_directed_rmat(ctx, mode):
