@@ -1,23 +1,32 @@
-"""Multi-GPU BFS: 1-D vertex partition, one process per GPU, per-level frontier exchange with torch.distributed.
+"""Multi-GPU BFS and SSSP: 1-D vertex partition, one process per GPU, per-level exchange.
 
 The reference has no multi-GPU path (its operators throw when ``context.size() != 1``,
 include/gunrock/framework/operators/advance/advance.hxx:125-128).  This module is the
 extension BASELINE.json asks for: rank r owns the contiguous vertex range [r*n/P, (r+1)*n/P) — its CSR rows
-with GLOBAL column ids and its slice of the depth array — and the frontier / visited sets are replicated
-1-bit-per-vertex maps (32 MiB at scale-28), so an exchange is a fixed-size collective:
+with GLOBAL column ids and its slice of the result array.
+
+BFS: the frontier / visited sets are replicated 1-bit-per-vertex maps (32 MiB at scale-28), so an exchange is a
+fixed-size collective:
 
   top-down level   local advance ORs unvisited neighbours into a global-length candidate map
                    -> all_to_all of the P candidate slices, owner ORs them        (n/8 bytes sent per rank)
   bottom-up level  owner walks the in-edges of its unvisited vertices against the replicated frontier map
                    (no candidate exchange at all)
   both             owner absorbs candidates (depth, visited), then ONE all_gather carries the new frontier
-                   slice together with the two Beamer counters (|F|, Σdeg F), so direction choice and
-                   termination are decided identically on every rank with no extra all_reduce.
+                   slice together with the two Beamer counters, so direction choice and termination are
+                   decided identically on every rank with no extra all_reduce.
 
-Local work runs in the CUDA library through ``ess_bfs_partition_step`` / ``ess_bfs_absorb``
-(include/essentials_b200.h).  The class takes the local step as a *backend* object so the exchange logic can
-be exercised on CPU with the gloo backend (tests/test_dist_gloo.py supplies a numpy backend); the product
-backend is :class:`CudaBackend` and there is no CPU fallback in it.
+SSSP: a replicated array of tentative distances; per round relax -> reduce_scatter(min) to the owners ->
+owner-side collect of the rows that improved (PartitionedSSSP below).
+
+Three drivers of the same logic:
+  * NativePartitionedBFS (.bfs / .sssp) — the product: whole loops in C++ (ess_dist_bfs / ess_dist_sssp,
+    essentials_b200/csrc/capi_dist.cu); the exchange runs in the library's own peer-memory kernels over NVLink
+    (IPC-mapped windows + epoch flags), NCCL bootstraps and is the fallback.
+  * PartitionedBFS / PartitionedSSSP with CudaBackend — the same loops over torch.distributed, calling the per-level
+    kernels through the C ABI (ess_bfs_partition_step / _pull / ess_bfs_absorb / ess_sssp_partition_*).
+  * the same classes with a numpy backend on the gloo backend — tests/test_dist_gloo.py, CPU only; the stand-in lives
+    in tests/, there is no CPU fallback in the product.
 """
 from __future__ import annotations
 
