@@ -75,6 +75,14 @@ int ess_tune(const char* knob, int value) {
     gunrock::operators::advance::near_far_ctas_per_sm() = value < 1 ? 1 : value;
     return 0;
   }
+  if (k == "advance_engine") {  // 1 = quad engine (128-bit loads, warp-autonomous rounds), 0 = round-1 scalar kernels
+    gunrock::operators::advance::kernels::advance_engine() = value;
+    return 0;
+  }
+  if (k == "pull_engine") {  // 1 = pull_chunk_kernel, 0 = pull_step_kernel
+    gunrock::operators::advance::kernels::pull_engine() = value;
+    return 0;
+  }
   if (k == "pull_hints") {
     gunrock::operators::advance::kernels::pull_hints_enabled() = value;
     return 0;

@@ -55,6 +55,7 @@ struct scratch_t {
     aux1 = 7,
     aux2 = 8,
     aux3 = 9,
+    quads = 10,       // 16-byte quads of column indices to expand (quad engine work domain)
     n_slots = 16
   };
 

@@ -32,6 +32,7 @@
 #include <gunrock/util/type_limits.hxx>
 #include <gunrock/framework/operators/configs.hxx>
 #include <gunrock/framework/operators/advance/kernels.cuh>
+#include <gunrock/framework/operators/advance/quad.cuh>
 #include <gunrock/framework/operators/advance/pull.cuh>
 #include <gunrock/framework/operators/advance/near_far.cuh>
 
@@ -113,6 +114,12 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
   const std::size_t prep_tiles = (nf + kernels::cta_threads * kernels::prep_items - 1) /
                                  (kernels::cta_threads * kernels::prep_items);
   const std::size_t item_ctas = (nf + kernels::cta_threads - 1) / kernels::cta_threads;
+  // quad engine (quad.cuh): 128-bit column / weight loads need 4-byte elements and 16-byte aligned arrays
+  using weight_t = typename graph_t::weight_type;
+  constexpr bool quad_types = sizeof(vertex_t) == 4 && sizeof(weight_t) == 4;
+  const bool quad = quad_types && kernels::advance_engine() != 0 &&
+                    (reinterpret_cast<std::uintptr_t>(A.indices) & 15u) == 0 &&
+                    (reinterpret_cast<std::uintptr_t>(A.values) & 15u) == 0;
 
   for (int attempt = 0; attempt < 3; ++attempt) {
     scratch.zero(stream);
@@ -144,51 +151,93 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
           // a frontier may repeat a hub (SSSP), so the only safe bound on deferred items is nf
           big_list = reinterpret_cast<vertex_t*>(scratch.temp(nf * sizeof(vertex_t)));
         }
-        const unsigned grid = gcuda::persistent_grid(ctx, item_ctas, 6);
-        if (guard)
-          kernels::block_mapped_kernel<graph_input, has_output, true, policy>
-              <<<grid, 256, 0, stream>>>(A, op, in, nf, out, C, capacity, visited, big_list);
-        else
-          kernels::block_mapped_kernel<graph_input, has_output, false, policy>
-              <<<grid, 256, 0, stream>>>(A, op, in, nf, out, C, capacity, visited, big_list);
-        if (big_list) {
-          // (the hub kernel's capacity guard reads Σdeg, which is 0 = "fits" when it was not needed)
-          kernels::big_list_kernel<has_output, policy><<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(
-              A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
-          prof.launches_total += 1;
+        if constexpr (quad_types) {
+          if (quad) {
+            const unsigned grid = gcuda::persistent_grid(ctx, item_ctas, 4);
+            if (guard)
+              kernels::block_mapped_quad_kernel<graph_input, has_output, true, policy>
+                  <<<grid, 256, 0, stream>>>(A, op, in, nf, out, C, capacity, visited, big_list);
+            else
+              kernels::block_mapped_quad_kernel<graph_input, has_output, false, policy>
+                  <<<grid, 256, 0, stream>>>(A, op, in, nf, out, C, capacity, visited, big_list);
+            if (big_list) {  // hubs: column indices staged through shared memory by the TMA unit
+              kernels::big_list_bulk_kernel<has_output, policy>
+                  <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 4), 256, 0, stream>>>(
+                      A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
+              prof.launches_total += 1;
+            }
+          }
+        }
+        if (!quad) {
+          const unsigned grid = gcuda::persistent_grid(ctx, item_ctas, 6);
+          if (guard)
+            kernels::block_mapped_kernel<graph_input, has_output, true, policy>
+                <<<grid, 256, 0, stream>>>(A, op, in, nf, out, C, capacity, visited, big_list);
+          else
+            kernels::block_mapped_kernel<graph_input, has_output, false, policy>
+                <<<grid, 256, 0, stream>>>(A, op, in, nf, out, C, capacity, visited, big_list);
+          if (big_list) {
+            // (the hub kernel's capacity guard reads Σdeg, which is 0 = "fits" when it was not needed)
+            kernels::big_list_kernel<has_output, policy>
+                <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(
+                    A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
+            prof.launches_total += 1;
+          }
         }
       }
       prof.end(stream);
     } else if constexpr (lb == load_balance_t::merge_path || lb == load_balance_t::merge_path_v2) {
-      if (nf <= std::size_t(kernels::tile_edges)) {  // tiny level: one launch, table built per CTA
+      const std::size_t small_limit = quad ? std::size_t(kernels::small_items) : std::size_t(kernels::tile_edges);
+      if (nf <= small_limit) {  // tiny level: one launch, table built per CTA
         const long long maxdeg = max_degree(ctx, A.offsets, A.n);
         long double bound = (long double)nf * (long double)maxdeg / kernels::tile_edges + 1;
         const std::size_t tiles = bound > 1e9L ? std::size_t(1000000000) : std::size_t(bound);
         prof.begin(profiler_t::push_expand, stream);
-        kernels::merge_path_small_kernel<graph_input, has_output, policy>
-            <<<gcuda::persistent_grid(ctx, tiles, 6), 256, 0, stream>>>(A, op, in, int(nf), out, C, capacity, visited);
+        if constexpr (quad_types) {
+          if (quad)
+            kernels::merge_path_small_quad_kernel<graph_input, has_output, policy>
+                <<<gcuda::persistent_grid(ctx, (tiles + 1) / 2, 4), 256, 0, stream>>>(A, op, in, int(nf), out, C,
+                                                                                      capacity, visited);
+        }
+        if (!quad)
+          kernels::merge_path_small_kernel<graph_input, has_output, policy>
+              <<<gcuda::persistent_grid(ctx, tiles, 6), 256, 0, stream>>>(A, op, in, int(nf), out, C, capacity,
+                                                                          visited);
         prof.end(stream);
       } else {
-      if (segments.size() < nf + 1) segments.resize(nf + 1);
-      gcuda::arena_layout_t layout;
-      const std::size_t at_src = layout.add((nf + 1) * sizeof(vertex_t));
-      const std::size_t at_beg = layout.add((nf + 1) * sizeof(edge_t));
-      const std::size_t at_state = layout.add(2 * prep_tiles * sizeof(b200::tile_word_t));
-      unsigned char* base = scratch.temp(layout.bytes);
-      auto* work_src = reinterpret_cast<vertex_t*>(base + at_src);
-      auto* work_beg = reinterpret_cast<edge_t*>(base + at_beg);
-      auto* state = reinterpret_cast<b200::tile_word_t*>(base + at_state);
-      edge_t* work_seg = raw_of(segments.data());
-      prof.begin(profiler_t::work_prepare, stream);
-      cudaMemsetAsync(state, 0, 2 * prep_tiles * sizeof(b200::tile_word_t), stream);
-      kernels::prepare_work_kernel<graph_input><<<gcuda::persistent_grid(ctx, prep_tiles, 6), 256, 0, stream>>>(
-          A.offsets, in, nf, work_src, work_beg, work_seg, state, state + prep_tiles, C);
-      prof.end(stream);
-      prof.begin(profiler_t::push_expand, stream);
-      kernels::merge_path_kernel<has_output, policy>
-          <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(A, op, work_src, work_beg, work_seg,
-                                                                                out, C, capacity, visited);
-      prof.end(stream);
+        if (segments.size() < nf + 1) segments.resize(nf + 1);
+        gcuda::arena_layout_t layout;
+        const std::size_t at_src = layout.add((nf + 1) * sizeof(vertex_t));
+        const std::size_t at_beg = layout.add((nf + 1) * sizeof(edge_t));
+        const std::size_t at_end = layout.add((nf + 1) * sizeof(edge_t));
+        const std::size_t at_state = layout.add(2 * prep_tiles * sizeof(b200::tile_word_t));
+        unsigned char* base = scratch.temp(layout.bytes);
+        auto* work_src = reinterpret_cast<vertex_t*>(base + at_src);
+        auto* work_beg = reinterpret_cast<edge_t*>(base + at_beg);
+        auto* work_end = reinterpret_cast<edge_t*>(base + at_end);
+        auto* state = reinterpret_cast<b200::tile_word_t*>(base + at_state);
+        edge_t* work_seg = raw_of(segments.data());
+        prof.begin(profiler_t::work_prepare, stream);
+        cudaMemsetAsync(state, 0, 2 * prep_tiles * sizeof(b200::tile_word_t), stream);
+        if (quad)
+          kernels::prepare_quads_kernel<graph_input><<<gcuda::persistent_grid(ctx, prep_tiles, 6), 256, 0, stream>>>(
+              A.offsets, in, nf, work_src, work_beg, work_end, work_seg, state, state + prep_tiles, C);
+        else
+          kernels::prepare_work_kernel<graph_input><<<gcuda::persistent_grid(ctx, prep_tiles, 6), 256, 0, stream>>>(
+              A.offsets, in, nf, work_src, work_beg, work_seg, state, state + prep_tiles, C);
+        prof.end(stream);
+        prof.begin(profiler_t::push_expand, stream);
+        if constexpr (quad_types) {
+          if (quad)
+            kernels::merge_path_quad_kernel<has_output, policy>
+                <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 4), 256, 0, stream>>>(
+                    A, op, work_src, work_beg, work_end, work_seg, out, C, capacity, visited);
+        }
+        if (!quad)
+          kernels::merge_path_kernel<has_output, policy>
+              <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(A, op, work_src, work_beg, work_seg,
+                                                                                    out, C, capacity, visited);
+        prof.end(stream);
       }
     } else if constexpr (lb == load_balance_t::bucketing) {
       gcuda::arena_layout_t layout;
@@ -207,11 +256,24 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
       kernels::thread_mapped_kernel<false, has_output, true, policy>
           <<<gcuda::persistent_grid(ctx, item_ctas, 8), 256, 0, stream>>>(A, op, small_list, 0, C + scratch_t::aux0, out,
                                                                         C, capacity, visited);
-      kernels::warp_mapped_kernel<has_output, policy>
-          <<<gcuda::persistent_grid(ctx, (nf + 7) / 8, 8), 256, 0, stream>>>(A, op, warp_list, C + scratch_t::aux1, out, C,
-                                                                            capacity, visited);
-      kernels::big_list_kernel<has_output, policy><<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(
-          A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
+      if constexpr (quad_types) {
+        if (quad) {
+          kernels::warp_mapped_quad_kernel<has_output, policy>
+              <<<gcuda::persistent_grid(ctx, (nf + 7) / 8, 4), 256, 0, stream>>>(A, op, warp_list, C + scratch_t::aux1,
+                                                                                out, C, capacity, visited);
+          kernels::big_list_bulk_kernel<has_output, policy>
+              <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 4), 256, 0, stream>>>(
+                  A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
+        }
+      }
+      if (!quad) {
+        kernels::warp_mapped_kernel<has_output, policy>
+            <<<gcuda::persistent_grid(ctx, (nf + 7) / 8, 8), 256, 0, stream>>>(A, op, warp_list, C + scratch_t::aux1, out,
+                                                                              C, capacity, visited);
+        kernels::big_list_kernel<has_output, policy>
+            <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 6), 256, 0, stream>>>(
+                A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
+      }
       prof.end(stream, 3);
     } else {
       error::throw_if_exception(cudaErrorUnknown, "Advance type not supported.");
@@ -303,13 +365,22 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
     auto& nxt = D.dense[D.dense_selector ^ 1];
     scratch.zero(stream);
     prof.begin(profiler_t::pull_step, stream);
-    kernels::pull_step_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 6), 256, 0, stream>>>(
-        in_adj, op, cur.data(), nxt.data(), D.visited.data(), scratch.d);
+    const bool chunked = kernels::pull_engine() != 0;
+    if (chunked) {
+      const std::size_t chunks = ((std::size_t(n) + 31) / 32 + kernels::pull_chunk_words - 1) / kernels::pull_chunk_words;
+      kernels::pull_chunk_kernel<<<gcuda::persistent_grid(ctx, (chunks + 7) / 8, 4), 256, 0, stream>>>(
+          in_adj, op, cur.data(), nxt.data(), D.visited.data(), scratch.d);
+    } else {
+      kernels::pull_step_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 6), 256, 0, stream>>>(
+          in_adj, op, cur.data(), nxt.data(), D.visited.data(), scratch.d);
+    }
     prof.end(stream);
     error::check_last("pull step");
     scratch.fetch(stream);
     next_vertices = (long long)scratch.h[scratch_t::out_count];
-    next_edges = (long long)scratch.h[scratch_t::aux2];
+    // the chunked kernel does not read row bounds of the vertices it adopts, so Σdeg of the next frontier is
+    // unknown while pulling; it is recomputed from the sparse list on the way back to top-down (below)
+    next_edges = chunked ? 0 : (long long)scratch.h[scratch_t::aux2];
     D.pull_vertices_scanned += (long long)scratch.h[scratch_t::aux0];
     D.pull_edges_inspected += (long long)scratch.h[scratch_t::aux1];
     D.dense_selector ^= 1;
@@ -317,10 +388,23 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
     output->set_number_of_elements(std::size_t(next_vertices));  // contents live in the dense map
     ++D.pull_steps;
   } else {
-    if (D.frontier_is_dense) {  // dense -> sparse
+    if (D.frontier_is_dense) {  // dense -> sparse, and Σdeg of the list (Beamer's m_f) in the same round trip
       prof.begin(profiler_t::dense_state, stream);
-      frontier::convert(D.dense[D.dense_selector], *input, ctx);
-      prof.end(stream);
+      auto& dense = D.dense[D.dense_selector];
+      const std::size_t upper = std::size_t(D.frontier_vertices);
+      if (input->get_capacity() < upper) input->reserve(upper);
+      scratch.zero(stream);
+      if (upper) {
+        frontier::kernels::gather_bits_kernel<<<gcuda::persistent_grid(ctx, (dense.words() + 255) / 256, 4), 256, 0,
+                                                stream>>>(dense.data(), dense.words(), input->data(),
+                                                          scratch.d + scratch_t::out_count);
+        kernels::mark_frontier_kernel<<<gcuda::persistent_grid(ctx, (upper + 255) / 256, 8), 256, 0, stream>>>(
+            out_adj.offsets, input->data(), upper, scratch.d + scratch_t::out_count, nullptr, scratch.d);
+      }
+      prof.end(stream, 2);
+      scratch.fetch(stream);
+      input->set_number_of_elements(std::size_t(scratch.h[scratch_t::out_count]));
+      D.frontier_edges = (long long)scratch.h[scratch_t::aux2];
       D.frontier_is_dense = false;
     }
     D.push_vertices_expanded += D.frontier_vertices;

@@ -181,6 +181,191 @@ __global__ void __launch_bounds__(256, 6)
   }
 }
 
+/// Shared-memory footprint of pull_chunk_kernel: one miss queue per warp. A chunk is 32 words = 1024 vertices; the
+/// queue holds every miss of one chunk plus the < 32 left over from the previous drain.
+constexpr int pull_chunk_words = 32;
+constexpr int pull_queue_cap = pull_chunk_words * 32 + 32;
+constexpr int pull_long_list = 64;  ///< adjacency lists longer than this are walked by the whole warp
+
+/**
+ * @brief One bottom-up level, second design (same contract as pull_step_kernel minus the Σdeg of the next
+ * frontier: counters[out_count] += |next frontier|, counters[aux0] += unvisited vertices probed,
+ * counters[aux1] += in-edges read).
+ *
+ * Why a second design. ncu on pull_step_kernel (profiles/r01c_pull_step_summary.txt): 223 warp instructions per
+ * 32-vertex word at 12-17 active lanes per instruction, DRAM traffic 3.1x the algorithmic bytes. A CPU model of the
+ * same levels (scale-20 Kronecker) shows why: the head hint resolves 82-99 % of the probed vertices, and the ones it
+ * does not resolve are almost all degree-1/2 vertices whose single neighbour is not in the frontier — so the warp
+ * spent most of its instructions in a walk loop that 2-5 of its 32 lanes were executing, and it paid the row
+ * bounds (2 x sizeof(edge_t) per vertex, coalesced) for every probed vertex although only the misses need them.
+ *   phase 1 (hint): a warp takes a chunk of 32 words; lane L loads visited word L (one coalesced 128-byte access),
+ *     then the chunk's words are processed four at a time: 4 coalesced head loads -> 4 frontier-bit probes ->
+ *     operator (owner-exclusive form) -> ballot. No row bounds are read. Lanes whose hint missed push their vertex
+ *     into the warp's shared-memory queue (ballot + popc, no atomics).
+ *   phase 2 (walk): after the chunk's words are written back, the queue is drained 32 vertices at a time with ALL
+ *     lanes busy: row bounds on demand, the list walked until the operator returns true. Lists longer than
+ *     pull_long_list are left to a warp-cooperative pass (coalesced 32-edge strides, ballot, first hit in list
+ *     order). Vertices found here are ORed into the (already written) next/visited words.
+ * Semantics: hinted in-neighbour first, then the in-edges in list order, until the operator returns true — as
+ * pull_step_kernel. Single-GPU form (A holds every row; visited/next are full-length).
+ */
+template <typename vertex_t, typename edge_t, typename weight_t, typename operator_t>
+__global__ void __launch_bounds__(256, 4)
+    pull_chunk_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op,
+                      const unsigned* __restrict__ frontier_bits, unsigned* __restrict__ next_bits,
+                      unsigned* __restrict__ visited, counter_t* counters) {
+  __shared__ unsigned s_queue[8][pull_queue_cap];
+  const unsigned lane = b200::lane_id();
+  unsigned* queue = s_queue[b200::warp_id()];
+  const unsigned n = unsigned(A.n);
+  const unsigned n_words = (n + 31u) >> 5;
+  const unsigned n_chunks = (n_words + pull_chunk_words - 1) / pull_chunk_words;
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  const bool hinted = A.head != nullptr;
+  unsigned found_vertices = 0, scanned = 0, inspected = 0;
+  unsigned queued = 0;  // warp-uniform
+  constexpr unsigned tried_flag = 0x80000000u;  // queue entry: the hint was offered to the operator and refused
+
+  // walks the adjacency of up to 32 queued vertices (one per lane), all lanes busy
+  auto drain = [&](unsigned take) {  // take <= 32, warp-uniform; consumes queue[queued - take .. queued)
+    unsigned entry = 0;
+    const bool mine = lane < take;
+    if (mine) entry = queue[queued - take + lane];
+    queued -= take;
+    const bool head_tried = (entry & tried_flag) != 0;
+    const vertex_t v = vertex_t(entry & ~tried_flag);
+    edge_t beg = 0, end = 0;
+    if (mine) {
+      beg = A.offsets[v];
+      end = A.offsets[v + 1];
+    }
+    const vertex_t head = (mine && head_tried) ? __ldg(A.head + v) : vertex_t(-1);
+    bool found = false;
+    const bool is_long = mine && (end - beg) > edge_t(pull_long_list);
+    if (mine && !is_long) {
+      for (edge_t e = beg; e < end && !found; ++e) {
+        ++inspected;
+        const vertex_t u = __ldg(A.indices + e);
+        if (u == head) continue;  // already offered to the operator
+        if ((__ldg(frontier_bits + (unsigned(u) >> 5)) >> (unsigned(u) & 31u)) & 1u) {
+          const weight_t weight = A.values ? __ldg(A.values + e) : weight_t(1);
+          found = call_pull(op, u, v, e, weight);
+        }
+      }
+    }
+    // long lists: the warp strides the list 32 edges at a time; candidates are offered in list order
+    unsigned long_lanes = __ballot_sync(b200::full_mask, is_long);
+    while (long_lanes) {
+      const int owner = __ffs(long_lanes) - 1;
+      long_lanes &= long_lanes - 1;
+      const vertex_t ov = __shfl_sync(b200::full_mask, v, owner);
+      const vertex_t ohead = __shfl_sync(b200::full_mask, head, owner);
+      const edge_t ob = __shfl_sync(b200::full_mask, beg, owner);
+      const edge_t oe = __shfl_sync(b200::full_mask, end, owner);
+      bool done = false;
+      for (edge_t e0 = ob; e0 < oe && !done; e0 += 32) {
+        const edge_t e = e0 + edge_t(lane);
+        vertex_t u = vertex_t(-1);
+        bool candidate = false;
+        if (e < oe) {
+          ++inspected;
+          u = __ldg(A.indices + e);
+          candidate = u != ohead && ((__ldg(frontier_bits + (unsigned(u) >> 5)) >> (unsigned(u) & 31u)) & 1u);
+        }
+        unsigned votes = __ballot_sync(b200::full_mask, candidate);
+        while (votes && !done) {
+          const int first = __ffs(votes) - 1;
+          votes &= votes - 1;
+          bool ok = false;
+          if (int(lane) == first) {
+            const weight_t weight = A.values ? __ldg(A.values + e) : weight_t(1);
+            ok = call_pull(op, u, ov, e, weight);
+          }
+          done = __shfl_sync(b200::full_mask, ok, first);
+        }
+      }
+      if (int(lane) == owner) found = done;
+    }
+    if (found) {
+      const unsigned bit = 1u << (unsigned(v) & 31u);
+      atomicOr(next_bits + (unsigned(v) >> 5), bit);
+      atomicOr(visited + (unsigned(v) >> 5), bit);
+      ++found_vertices;
+    }
+  };
+
+  for (unsigned chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < n_chunks; chunk += warps) {
+    const unsigned w_mine = chunk * pull_chunk_words + lane;
+    const unsigned seen_mine = w_mine < n_words ? visited[w_mine] : 0xffffffffu;
+    unsigned fresh_mine = 0;
+    // groups of 4 consecutive words with at least one unvisited vertex
+    unsigned open_words = __ballot_sync(b200::full_mask, seen_mine != 0xffffffffu);
+#pragma unroll 1
+    for (int g = 0; g < pull_chunk_words / 4; ++g) {
+      if (!((open_words >> (4 * g)) & 0xfu)) continue;  // warp-uniform
+      unsigned seen[4];
+      vertex_t head[4];
+      unsigned probe[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        seen[k] = __shfl_sync(b200::full_mask, seen_mine, 4 * g + k);
+        head[k] = vertex_t(-1);
+        if (!((seen[k] >> lane) & 1u)) {
+          const unsigned v = ((chunk * pull_chunk_words + 4 * g + k) << 5) + lane;
+          if (hinted) head[k] = __ldg(A.head + v);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) probe[k] = head[k] >= 0 ? __ldg(frontier_bits + (unsigned(head[k]) >> 5)) : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool open = !((seen[k] >> lane) & 1u);
+        const vertex_t v = vertex_t(((chunk * pull_chunk_words + 4 * g + k) << 5) + lane);
+        bool found = false, tried = false;
+        if (open) {
+          ++scanned;
+          if (head[k] >= 0 && ((probe[k] >> (unsigned(head[k]) & 31u)) & 1u)) {
+            const edge_t edge = __ldg(A.head_edge + v);
+            const weight_t weight = A.values ? __ldg(A.values + edge) : weight_t(1);
+            found = call_pull(op, head[k], v, edge, weight);
+            tried = true;
+          }
+        }
+        const unsigned fresh = __ballot_sync(b200::full_mask, found);
+        if (int(lane) == 4 * g + k) fresh_mine = fresh;
+        const bool miss = open && !found;
+        const unsigned misses = __ballot_sync(b200::full_mask, miss);
+        if (miss) queue[queued + __popc(misses & b200::lanes_below(lane))] = unsigned(v) | (tried ? tried_flag : 0u);
+        queued += __popc(misses);
+      }
+    }
+    if (w_mine < n_words) {
+      next_bits[w_mine] = fresh_mine;
+      if (fresh_mine) visited[w_mine] = seen_mine | fresh_mine;
+    }
+    found_vertices += __popc(fresh_mine);
+    __syncwarp();  // queue writes and the word stores above precede the drain's reads / atomics
+    while (queued >= 32) drain(32);
+  }
+  __syncwarp();
+  if (queued) drain(queued);
+
+  found_vertices = b200::warp_sum(found_vertices);
+  scanned = b200::warp_sum(scanned);
+  inspected = b200::warp_sum(inspected);
+  if (lane == 0) {
+    if (found_vertices) atomicAdd(counters + scratch_t::out_count, counter_t(found_vertices));
+    if (scanned) atomicAdd(counters + scratch_t::aux0, counter_t(scanned));
+    if (inspected) atomicAdd(counters + scratch_t::aux1, counter_t(inspected));
+  }
+}
+
+/// Development knob (ess_tune "pull_engine"): 1 = pull_chunk_kernel (default), 0 = pull_step_kernel.
+inline int& pull_engine() {
+  static int engine = 1;
+  return engine;
+}
+
 /// Development knob: use the per-vertex head hints when the graph carries them (default on).
 inline int& pull_hints_enabled() {
   static int enabled = 1;

@@ -18,6 +18,7 @@ ap.add_argument("--pull-variants", default="")
 ap.add_argument("--hints", default="1")
 ap.add_argument("--alphas", default="0")
 ap.add_argument("--betas", default="0")
+ap.add_argument("--engines", default="11", help="comma list of <advance_engine><pull_engine> digits, e.g. 00,11")
 args = ap.parse_args()
 
 t = time.time()
@@ -32,12 +33,14 @@ base = None
 runs = [(v, None) for v in args.variants.split(",")]
 if args.pull_variants:
     runs = [(v, int(pv)) for pv in args.pull_variants.split(",") for v in args.variants.split(",")]
-runs = [(v, pv, int(h), float(a), float(b)) for (v, pv) in runs for h in args.hints.split(",")
-        for a in args.alphas.split(",") for b in args.betas.split(",")]
-for variant, pv, hints, alpha, beta in runs:
+runs = [(v, pv, int(h), float(a), float(b), eng) for eng in args.engines.split(",") for (v, pv) in runs
+        for h in args.hints.split(",") for a in args.alphas.split(",") for b in args.betas.split(",")]
+for variant, pv, hints, alpha, beta, eng in runs:
     lb, direction = variant.split(":")
     ess.tune("pull_hints", hints)
-    variant = f"{variant}/pv{pv}/h{hints}/a{alpha:g}/b{beta:g}"
+    ess.tune("advance_engine", int(eng[0]))
+    ess.tune("pull_engine", int(eng[1]))
+    variant = f"{variant}/eng{eng}/h{hints}/a{alpha:g}/b{beta:g}"
     for s in srcs:
         ctx.profile(True)
         depth, info = ess.bfs(ctx, g, s, lb=lb, direction=direction, alpha=alpha, beta=beta)
