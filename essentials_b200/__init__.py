@@ -36,13 +36,15 @@ class EssentialsError(RuntimeError):
 
 class RunInfo(Structure):
     _fields_ = [("enact_ms", c_float), ("iterations", c_int32), ("pull_steps", c_int32), ("push_steps", c_int32),
-                ("reserved", c_int64 * 4)]
+                ("reserved", c_int64 * 8)]
 
     def as_dict(self):
         return {"enact_ms": float(self.enact_ms), "iterations": int(self.iterations),
                 "pull_steps": int(self.pull_steps), "push_steps": int(self.push_steps),
                 "pull_vertices": int(self.reserved[0]), "pull_edges": int(self.reserved[1]),
-                "push_vertices": int(self.reserved[2]), "push_edges": int(self.reserved[3])}
+                "push_vertices": int(self.reserved[2]), "push_edges": int(self.reserved[3]),
+                "pull_misses": int(self.reserved[4]), "pull_found": int(self.reserved[5]),
+                "push_found": int(self.reserved[6])}
 
 
 _SIGNATURES = {

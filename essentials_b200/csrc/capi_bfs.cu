@@ -13,11 +13,11 @@ int run_bfs(ess_context_t ctx, graph_t& G, int32_t source, int32_t* d_depth, flo
   if (beta > 0) props.direction_beta = beta;
   int pulls = 0, iters = 0;
   int32_t src = source;
-  long long stats[4] = {0, 0, 0, 0};
+  long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float ms = bfs::run<lb, dir>(G, src, d_depth, (int32_t*)nullptr, ctx->ctx, props, &pulls, &iters, stats);
   ess::fill_info(info, ms, iters, pulls, iters - pulls);
   if (info)
-    for (int i = 0; i < 4; ++i) info->reserved[i] = stats[i];
+    for (int i = 0; i < 8; ++i) info->reserved[i] = stats[i];
   return 0;
 }
 }  // namespace

@@ -83,6 +83,10 @@ int ess_tune(const char* knob, int value) {
     gunrock::operators::advance::kernels::pull_engine() = value;
     return 0;
   }
+  if (k == "near_far_cluster") {  // 1 = small levels of execute_near_far run in one thread-block cluster
+    gunrock::operators::advance::near_far_cluster_enabled() = value;
+    return 0;
+  }
   if (k == "pull_hints") {
     gunrock::operators::advance::kernels::pull_hints_enabled() = value;
     return 0;

@@ -53,8 +53,10 @@ typedef struct ess_run_info {
   int32_t iterations; /* enactor_t::iteration at convergence */
   int32_t pull_steps; /* direction-optimised BFS: levels run bottom-up */
   int32_t push_steps; /* direction-optimised BFS: levels run top-down */
-  int64_t reserved[4]; /* ess_bfs/OPTIMIZED work accounting: [0] vertices walked bottom-up, [1] in-edges read
-                          bottom-up (early exit counted), [2] vertices and [3] out-edges expanded top-down */
+  int64_t reserved[8]; /* ess_bfs/OPTIMIZED work accounting: [0] vertices probed bottom-up, [1] in-edges read
+                          bottom-up (early exit counted), [2] vertices and [3] out-edges expanded top-down,
+                          [4] bottom-up hint misses (adjacency walked), [5] vertices adopted bottom-up,
+                          [6] vertices claimed top-down; other entry points document their own use */
 } ess_run_info;
 
 ESS_API const char* ess_last_error(void);

@@ -127,6 +127,9 @@ float run(graph_t& G, typename graph_t::vertex_type& single_source, typename gra
     work_stats[1] = enactor.direction.pull_edges_inspected;
     work_stats[2] = enactor.direction.push_vertices_expanded;
     work_stats[3] = enactor.direction.push_edges_expanded;
+    work_stats[4] = enactor.direction.pull_hint_misses;     // [4] bottom-up hint misses (lists walked)
+    work_stats[5] = enactor.direction.pull_vertices_found;  // [5] vertices adopted bottom-up
+    work_stats[6] = enactor.direction.push_vertices_found;  // [6] vertices claimed top-down
   }
   return ms;
 }

@@ -25,6 +25,8 @@
  */
 #pragma once
 
+#include <cmath>
+
 #include <gunrock/algorithms/algorithms.hxx>
 
 namespace gunrock {
@@ -320,6 +322,9 @@ float run_delta(graph_t& G, typename graph_t::vertex_type single_source, typenam
       std::memcpy(&nearest, &bits, sizeof(float));
       const float next = (std::floor(nearest / delta) + 1.f) * delta;
       threshold = next > threshold ? next : threshold + delta;
+      // strict progress: with distances above ~2^24 * delta both forms can round to <= nearest and the round
+      // would select nothing for ever; the selection is `dist < threshold`, so step just past the nearest key
+      if (!(threshold > nearest)) threshold = std::nextafter(nearest, std::numeric_limits<float>::infinity());
       if (!(threshold < std::numeric_limits<float>::max())) threshold = std::numeric_limits<float>::max();
       ++advances;
       continue;

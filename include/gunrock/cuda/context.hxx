@@ -14,6 +14,7 @@
 #pragma once
 
 #include <cstdint>
+#include <unordered_map>
 #include <vector>
 #include <cuda_runtime_api.h>
 #include <thrust/execution_policy.h>
@@ -251,6 +252,20 @@ class standard_context_t {
     _scratch.init();
     return _scratch;
   }
+  /// CTAs of `threads` threads of `kernel` that fit on one SM (occupancy API, cached per kernel).
+  template <typename kernel_t>
+  int resident_ctas(kernel_t kernel, int threads) {
+    const void* key = reinterpret_cast<const void*>(kernel);
+    auto it = _occupancy.find(key);
+    if (it != _occupancy.end()) return it->second;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 1;
+    }
+    _occupancy.emplace(key, per_sm);
+    return per_sm;
+  }
   profiler_t& profiler() { return _profiler; }
 
  private:
@@ -268,6 +283,7 @@ class standard_context_t {
   util::timer_t _timer;
   scratch_t _scratch;
   profiler_t _profiler;
+  std::unordered_map<const void*, int> _occupancy;
 };
 
 inline void standard_context_t::print_properties() {

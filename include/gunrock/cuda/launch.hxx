@@ -50,5 +50,15 @@ inline unsigned persistent_grid(standard_context_t& ctx, std::size_t work_ctas, 
   return unsigned(g ? g : 1);
 }
 
+/// Grid of a persistent kernel: every CTA the device can hold at once (SMs x occupancy of `kernel`), at most
+/// `max_per_sm` per SM and never more than `work_ctas`.
+template <typename kernel_t>
+inline unsigned full_grid(standard_context_t& ctx, kernel_t kernel, std::size_t work_ctas = ~std::size_t(0),
+                          int max_per_sm = 8, int threads = 256) {
+  int per_sm = ctx.resident_ctas(kernel, threads);
+  if (per_sm > max_per_sm) per_sm = max_per_sm;
+  return persistent_grid(ctx, work_ctas, per_sm);
+}
+
 }  // namespace gcuda
 }  // namespace gunrock

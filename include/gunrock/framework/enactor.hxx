@@ -63,6 +63,9 @@ struct direction_state_t {
   long long pull_edges_inspected = 0;   ///< in-edges read by bottom-up levels (early exit counted)
   long long push_edges_expanded = 0;    ///< out-edges expanded by top-down levels
   long long push_vertices_expanded = 0; ///< frontier vertices expanded by top-down levels
+  long long pull_hint_misses = 0;       ///< bottom-up: probed vertices whose hint missed (adjacency walked)
+  long long pull_vertices_found = 0;    ///< vertices adopted by bottom-up levels
+  long long push_vertices_found = 0;    ///< vertices claimed by top-down levels
   /// Size the three bitmaps for n vertices (idempotent; call before enact() to keep it out of the timed loop).
   void allocate(std::size_t n, gcuda::stream_t stream = 0) {
     if (visited.get_universe() == n) return;
@@ -78,6 +81,7 @@ struct direction_state_t {
     frontier_edges = unexplored_edges = frontier_vertices = previous_frontier_vertices = 0;
     pull_steps = push_steps = 0;
     pull_vertices_scanned = pull_edges_inspected = push_edges_expanded = push_vertices_expanded = 0;
+    pull_hint_misses = pull_vertices_found = push_vertices_found = 0;
   }
 };
 

@@ -33,6 +33,18 @@ namespace gunrock {
 namespace frontier {
 using namespace memory;
 
+/// CTAs of a grid-stride streaming kernel over `items` elements: SMs of the current device x 8, at most.
+inline unsigned stream_ctas(std::size_t items) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 1;
+  }
+  const std::size_t cap = std::size_t(sms) * 8, c = (items + 255) / 256;
+  return unsigned(c < cap ? (c ? c : 1) : cap);
+}
+
 namespace kernels {
 
 template <typename type_t>
@@ -232,10 +244,7 @@ class vector_frontier_t {
   }
 
  protected:
-  static unsigned launch_ctas(std::size_t items) {
-    std::size_t c = (items + 255) / 256;
-    return unsigned(c < 148 * 8 ? (c ? c : 1) : 148 * 8);
-  }
+  static unsigned launch_ctas(std::size_t items) { return stream_ctas(items); }
   void reserve_exact(std::size_t n) {
     p_storage->grow(n, num_elements < p_storage->cap ? num_elements : p_storage->cap);
     raw_ptr = p_storage->ptr;
@@ -288,7 +297,7 @@ class bitmap_frontier_t {
   void resize(std::size_t size, gcuda::stream_t stream = 0) {
     std::size_t old_words = words();
     universe = size;
-    p_storage->grow(words() + 1, old_words);
+    p_storage->grow(words() + 4, old_words);  // +1 padding word, +2..3 the size-query counter (8-byte aligned)
     raw_ptr = p_storage->ptr;
     if (words() + 1 > old_words)
       cudaMemsetAsync(raw_ptr + old_words, 0, (words() + 1 - old_words) * sizeof(word_t), stream);
@@ -326,13 +335,13 @@ class bitmap_frontier_t {
   /// Number of active ids; runs a popcount kernel only if the map changed since the last query.
   std::size_t get_number_of_elements(gcuda::stream_t stream = 0) {
     if (dirty) {
-      b200::counter_t* d_total = memory::allocate<b200::counter_t>(sizeof(b200::counter_t));
+      // the counter lives in the spare word pair behind the map (storage is words() + 3): no allocation per query
+      auto* d_total = reinterpret_cast<b200::counter_t*>(raw_ptr + ((words() + 2) & ~std::size_t(1)));
       cudaMemsetAsync(d_total, 0, sizeof(b200::counter_t), stream);
-      kernels::popcount_kernel<<<148 * 4, 256, 0, stream>>>(raw_ptr, words(), d_total);
+      kernels::popcount_kernel<<<stream_ctas(words()), 256, 0, stream>>>(raw_ptr, words(), d_total);
       b200::counter_t h = 0;
       cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, stream);
       cudaStreamSynchronize(stream);
-      memory::free(d_total);
       cached_count = std::size_t(h);
       dirty = false;
     }
@@ -398,8 +407,8 @@ void convert(frontier_t<V, E, K, frontier_view_t::vector>& sparse, frontier_t<V,
   std::size_t count = sparse.get_number_of_elements();
   if (count) {
     std::size_t ctas = (count + 255) / 256;
-    kernels::scatter_bits_kernel<<<unsigned(ctas < 148 * 8 ? ctas : 148 * 8), 256, 0, stream>>>(sparse.data(), count,
-                                                                                                  dense.data());
+    (void)ctas;
+    kernels::scatter_bits_kernel<<<stream_ctas(count), 256, 0, stream>>>(sparse.data(), count, dense.data());
   }
   dense.mark_dirty();
 }
@@ -415,8 +424,8 @@ void convert(frontier_t<V, E, K, DV>& dense, frontier_t<V, E, K, frontier_view_t
   if (sparse.get_capacity() < upper) sparse.reserve(upper);
   scratch.zero(stream);
   if (upper)
-    kernels::gather_bits_kernel<<<148 * 4, 256, 0, stream>>>(dense.data(), dense.words(), sparse.data(),
-                                                              scratch.d + gcuda::scratch_t::out_count);
+    kernels::gather_bits_kernel<<<gcuda::persistent_grid(context, (dense.words() + 255) / 256, 4), 256, 0, stream>>>(
+        dense.data(), dense.words(), sparse.data(), scratch.d + gcuda::scratch_t::out_count);
   scratch.fetch(stream);
   sparse.set_number_of_elements(std::size_t(scratch.h[gcuda::scratch_t::out_count]));
 }

@@ -121,6 +121,12 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
                     (reinterpret_cast<std::uintptr_t>(A.indices) & 15u) == 0 &&
                     (reinterpret_cast<std::uintptr_t>(A.values) & 15u) == 0;
 
+  // max_degree() may run a kernel and fetch() the counters on its first call per graph: resolve it BEFORE the
+  // counters of this call are zeroed, so `clean` never claims a block that kernels of this call have written
+  long long maxdeg = 0;
+  if constexpr (lb == load_balance_t::thread_mapped || lb == load_balance_t::block_mapped ||
+                lb == load_balance_t::merge_path || lb == load_balance_t::merge_path_v2)
+    maxdeg = max_degree(ctx, A.offsets, A.n);
   for (int attempt = 0; attempt < 3; ++attempt) {
     scratch.zero(stream);
     vertex_t* out = has_output ? output->data() : nullptr;
@@ -128,7 +134,6 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
     counter_t* C = scratch.d;
 
     if constexpr (lb == load_balance_t::thread_mapped || lb == load_balance_t::block_mapped) {
-      const long long maxdeg = max_degree(ctx, A.offsets, A.n);
       const bool guard = has_output && (long double)(nf) * (long double)(maxdeg) > (long double)(capacity);
       if (guard) {
         prof.begin(profiler_t::work_prepare, stream);
@@ -153,17 +158,21 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
         }
         if constexpr (quad_types) {
           if (quad) {
-            const unsigned grid = gcuda::persistent_grid(ctx, item_ctas, 4);
-            if (guard)
-              kernels::block_mapped_quad_kernel<graph_input, has_output, true, policy>
-                  <<<grid, 256, 0, stream>>>(A, op, in, nf, out, C, capacity, visited, big_list);
-            else
-              kernels::block_mapped_quad_kernel<graph_input, has_output, false, policy>
-                  <<<grid, 256, 0, stream>>>(A, op, in, nf, out, C, capacity, visited, big_list);
+            if (guard) {
+              auto kernel = kernels::block_mapped_quad_kernel<graph_input, has_output, true, policy, vertex_t, edge_t,
+                                                              weight_t, operator_t>;
+              kernel<<<gcuda::full_grid(ctx, kernel, item_ctas), 256, 0, stream>>>(A, op, in, nf, out, C, capacity,
+                                                                                   visited, big_list);
+            } else {
+              auto kernel = kernels::block_mapped_quad_kernel<graph_input, has_output, false, policy, vertex_t, edge_t,
+                                                              weight_t, operator_t>;
+              kernel<<<gcuda::full_grid(ctx, kernel, item_ctas), 256, 0, stream>>>(A, op, in, nf, out, C, capacity,
+                                                                                   visited, big_list);
+            }
             if (big_list) {  // hubs: column indices staged through shared memory by the TMA unit
-              kernels::big_list_bulk_kernel<has_output, policy>
-                  <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 4), 256, 0, stream>>>(
-                      A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
+              auto kernel = kernels::big_list_bulk_kernel<has_output, policy, vertex_t, edge_t, weight_t, operator_t>;
+              kernel<<<gcuda::full_grid(ctx, kernel), 256, 0, stream>>>(A, op, big_list, C + scratch_t::big_count, out,
+                                                                        C, capacity, visited);
               prof.launches_total += 1;
             }
           }
@@ -189,15 +198,16 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
     } else if constexpr (lb == load_balance_t::merge_path || lb == load_balance_t::merge_path_v2) {
       const std::size_t small_limit = quad ? std::size_t(kernels::small_items) : std::size_t(kernels::tile_edges);
       if (nf <= small_limit) {  // tiny level: one launch, table built per CTA
-        const long long maxdeg = max_degree(ctx, A.offsets, A.n);
         long double bound = (long double)nf * (long double)maxdeg / kernels::tile_edges + 1;
         const std::size_t tiles = bound > 1e9L ? std::size_t(1000000000) : std::size_t(bound);
         prof.begin(profiler_t::push_expand, stream);
         if constexpr (quad_types) {
-          if (quad)
-            kernels::merge_path_small_quad_kernel<graph_input, has_output, policy>
-                <<<gcuda::persistent_grid(ctx, (tiles + 1) / 2, 4), 256, 0, stream>>>(A, op, in, int(nf), out, C,
-                                                                                      capacity, visited);
+          if (quad) {
+            auto kernel = kernels::merge_path_small_quad_kernel<graph_input, has_output, policy, vertex_t, edge_t,
+                                                                weight_t, operator_t>;
+            kernel<<<gcuda::full_grid(ctx, kernel, (tiles + 1) / 2), 256, 0, stream>>>(A, op, in, int(nf), out, C,
+                                                                                       capacity, visited);
+          }
         }
         if (!quad)
           kernels::merge_path_small_kernel<graph_input, has_output, policy>
@@ -228,10 +238,11 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
         prof.end(stream);
         prof.begin(profiler_t::push_expand, stream);
         if constexpr (quad_types) {
-          if (quad)
-            kernels::merge_path_quad_kernel<has_output, policy>
-                <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 4), 256, 0, stream>>>(
-                    A, op, work_src, work_beg, work_end, work_seg, out, C, capacity, visited);
+          if (quad) {
+            auto kernel = kernels::merge_path_quad_kernel<has_output, policy, vertex_t, edge_t, weight_t, operator_t>;
+            kernel<<<gcuda::full_grid(ctx, kernel), 256, 0, stream>>>(A, op, work_src, work_beg, work_end, work_seg,
+                                                                      out, C, capacity, visited);
+          }
         }
         if (!quad)
           kernels::merge_path_kernel<has_output, policy>
@@ -258,12 +269,12 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
                                                                         C, capacity, visited);
       if constexpr (quad_types) {
         if (quad) {
-          kernels::warp_mapped_quad_kernel<has_output, policy>
-              <<<gcuda::persistent_grid(ctx, (nf + 7) / 8, 4), 256, 0, stream>>>(A, op, warp_list, C + scratch_t::aux1,
-                                                                                out, C, capacity, visited);
-          kernels::big_list_bulk_kernel<has_output, policy>
-              <<<gcuda::persistent_grid(ctx, ~std::size_t(0), 4), 256, 0, stream>>>(
-                  A, op, big_list, C + scratch_t::big_count, out, C, capacity, visited);
+          auto warp_kernel = kernels::warp_mapped_quad_kernel<has_output, policy, vertex_t, edge_t, weight_t, operator_t>;
+          warp_kernel<<<gcuda::full_grid(ctx, warp_kernel, (nf + 7) / 8), 256, 0, stream>>>(
+              A, op, warp_list, C + scratch_t::aux1, out, C, capacity, visited);
+          auto hub_kernel = kernels::big_list_bulk_kernel<has_output, policy, vertex_t, edge_t, weight_t, operator_t>;
+          hub_kernel<<<gcuda::full_grid(ctx, hub_kernel), 256, 0, stream>>>(A, op, big_list, C + scratch_t::big_count,
+                                                                            out, C, capacity, visited);
         }
       }
       if (!quad) {
@@ -281,7 +292,10 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
     epilogue(C, out);  // extra kernels that consume the device-side output count before the one sync
     error::check_last("advance launch");
     if constexpr (!has_output)
-      if (scratch.async_when_no_output) return;  // nothing to report; counters are re-zeroed by the next zero()
+      if (scratch.async_when_no_output) {  // nothing to report; the next zero() must really clear the counters
+        scratch.clean = false;
+        return;
+      }
     scratch.fetch(stream);
     if constexpr (has_output) {
       if (scratch.h[scratch_t::overflow]) {  // nothing was expanded: grow and go again
@@ -368,8 +382,9 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
     const bool chunked = kernels::pull_engine() != 0;
     if (chunked) {
       const std::size_t chunks = ((std::size_t(n) + 31) / 32 + kernels::pull_chunk_words - 1) / kernels::pull_chunk_words;
-      kernels::pull_chunk_kernel<<<gcuda::persistent_grid(ctx, (chunks + 7) / 8, 4), 256, 0, stream>>>(
-          in_adj, op, cur.data(), nxt.data(), D.visited.data(), scratch.d);
+      auto kernel = kernels::pull_chunk_kernel<vertex_t, edge_t, typename graph_t::weight_type, operator_t>;
+      kernel<<<gcuda::full_grid(ctx, kernel, (chunks + 7) / 8), 256, 0, stream>>>(in_adj, op, cur.data(), nxt.data(),
+                                                                                  D.visited.data(), scratch.d);
     } else {
       kernels::pull_step_kernel<<<gcuda::persistent_grid(ctx, (std::size_t(n) + 255) / 256, 6), 256, 0, stream>>>(
           in_adj, op, cur.data(), nxt.data(), D.visited.data(), scratch.d);
@@ -383,6 +398,8 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
     next_edges = chunked ? 0 : (long long)scratch.h[scratch_t::aux2];
     D.pull_vertices_scanned += (long long)scratch.h[scratch_t::aux0];
     D.pull_edges_inspected += (long long)scratch.h[scratch_t::aux1];
+    if (chunked) D.pull_hint_misses += (long long)scratch.h[scratch_t::aux2];
+    D.pull_vertices_found += next_vertices;
     D.dense_selector ^= 1;
     D.dense[D.dense_selector].set_number_of_elements(std::size_t(next_vertices));
     output->set_number_of_elements(std::size_t(next_vertices));  // contents live in the dense map
@@ -410,12 +427,20 @@ void optimized(graph_t& G, enactor_type* E, operator_t op, gcuda::standard_conte
     D.push_vertices_expanded += D.frontier_vertices;
     D.push_edges_expanded += D.frontier_edges;
     grow_output(output, std::size_t(n));
-    // Σdeg of the new frontier (Beamer's m_f) is accumulated inside the expansion kernels (test-and-set
-    // policy adds the out-degree of every vertex it marks), so the level costs a single synchronisation.
+    // Σdeg of the new frontier (Beamer's m_f): one parallel pass over the output list, enqueued behind the
+    // expansion kernels and in front of the level's single host round trip (it reads the list length from the
+    // device counter the expansion just produced).
+    const auto* degree_offsets = out_adj.offsets;
+    auto degree_sum = [&](counter_t* C, vertex_t* out) {
+      kernels::mark_frontier_kernel<<<gcuda::persistent_grid(ctx, ~std::size_t(0), 4), 256, 0, stream>>>(
+          degree_offsets, out, 0, C + scratch_t::out_count, nullptr, C);
+      prof.launches_total += 1;
+    };
     expand<lb, false, input_type, output_type, visit_t::test_and_set>(G, op, input, output, E->scanned_work_domain, ctx,
-                                                                     D.visited.data());
+                                                                     D.visited.data(), degree_sum);
     next_vertices = (long long)output->get_number_of_elements();
     next_edges = next_vertices ? (long long)scratch.h[scratch_t::aux2] : 0;
+    D.push_vertices_found += next_vertices;
     ++D.push_steps;
   }
   D.previous_frontier_vertices = D.frontier_vertices;

@@ -46,7 +46,7 @@ constexpr int cta_threads = 256;
 constexpr int tile_items = 4;                         // edges per thread per round
 constexpr int tile_edges = cta_threads * tile_items;  // 1024 edges per CTA round
 constexpr int prep_items = 4;                         // frontier items per thread in the preparation pass
-constexpr long long big_degree = 8192;                // adjacency lists this long are expanded grid-wide
+constexpr long long big_degree = 4096;                // adjacency lists this long are expanded grid-wide
 constexpr int warp_degree = 32;                       // bucketing: lists at least this long get a warp
 
 /// Visited-bitmap handling of an advance: `none` = reference semantics (operator runs on every edge);
@@ -54,6 +54,13 @@ constexpr int warp_degree = 32;                       // bucketing: lists at lea
 /// `unique_output` = fused uniquify: the operator still runs on every edge, but a neighbour it keeps is emitted
 /// only by the first edge that sets its bit in the (per-call, initially clear) bitmap.
 enum class visit_t { none, test_and_set, unique_output };
+
+/// Σdeg of the vertices a test_and_set advance claims (Beamer's m_f of the next frontier) used to be accumulated
+/// inside the expansion kernels: two dependent random row-bound loads at the END of every discovery's chain
+/// (probe -> test-and-set -> operator), which ncu showed as the long-scoreboard tail of the heavy top-down level.
+/// It is now a separate, fully parallel pass over the output list (mark_frontier_kernel, enqueued by
+/// detail::optimized before the level's one host round trip).
+constexpr bool count_fresh_edges_in_kernel = false;
 
 /// `fresh_edges` (test_and_set only) accumulates the out-degree of every vertex this thread adds to the
 /// visited set: Σdeg of the next frontier is Beamer's m_f, needed by the push/pull switch.
@@ -70,7 +77,8 @@ __device__ __forceinline__ bool visit_edge(const graph::adjacency_t<vertex_t, ed
     if (keep) {
       const unsigned bit = 1u << (unsigned(neighbor) & 31u);
       keep = !(atomicOr(&visited[unsigned(neighbor) >> 5], bit) & bit);
-      if (keep) fresh_edges += counter_t(A.offsets[neighbor + 1] - A.offsets[neighbor]);
+      if constexpr (count_fresh_edges_in_kernel)
+        if (keep) fresh_edges += counter_t(A.offsets[neighbor + 1] - A.offsets[neighbor]);
     }
   }
   if constexpr (policy == visit_t::unique_output) {
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(256)
 /// End-of-kernel flush of a thread's fresh_edges into counters[aux2] (one atomic per warp).
 template <visit_t policy>
 __device__ __forceinline__ void flush_fresh_edges(counter_t fresh_edges, counter_t* counters) {
-  if constexpr (policy == visit_t::test_and_set) {
+  if constexpr (policy == visit_t::test_and_set && count_fresh_edges_in_kernel) {
     __syncwarp();
     fresh_edges = b200::warp_sum(fresh_edges);
     if (b200::lane_id() == 0 && fresh_edges) atomicAdd(counters + scratch_t::aux2, fresh_edges);
@@ -172,16 +180,18 @@ __device__ __forceinline__ void expand_tile(const graph::adjacency_t<vertex_t, e
           const weight_t weight = A.values ? __ldg(A.values + eid[i]) : weight_t(1);
           if (call_pull(op, src[i], nbr[i], eid[i], weight)) keep |= 1u << i;
         }
-      edge_t lo[tile_items], hi[tile_items];
+      if constexpr (count_fresh_edges_in_kernel) {
+        edge_t lo[tile_items], hi[tile_items];
 #pragma unroll
-      for (int i = 0; i < tile_items; ++i)
-        if (keep & (1u << i)) {
-          lo[i] = A.offsets[nbr[i]];
-          hi[i] = A.offsets[nbr[i] + 1];
-        }
+        for (int i = 0; i < tile_items; ++i)
+          if (keep & (1u << i)) {
+            lo[i] = A.offsets[nbr[i]];
+            hi[i] = A.offsets[nbr[i] + 1];
+          }
 #pragma unroll
-      for (int i = 0; i < tile_items; ++i)
-        if (keep & (1u << i)) fresh_edges += counter_t(hi[i] - lo[i]);
+        for (int i = 0; i < tile_items; ++i)
+          if (keep & (1u << i)) fresh_edges += counter_t(hi[i] - lo[i]);
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < tile_items; ++i)

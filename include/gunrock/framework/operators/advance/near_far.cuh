@@ -50,6 +50,15 @@ struct near_far_state_t {
   int levels;    ///< near levels executed
   int splits;    ///< far-pile splits executed
   int overflow;  ///< a queue ran out of capacity (impossible with capacity n thanks to the stamps; checked anyway)
+  int level;     ///< next near level to run (lets the grid-wide and the cluster kernel hand the run to each other)
+  int exit_reason;  ///< why the kernel returned: see near_far_exit_t
+};
+
+/// Why a near-far kernel returned to the host.
+enum near_far_exit_t : int {
+  near_far_done = 0,       ///< near queue and far pile empty (or max_levels reached)
+  near_far_grew = 1,       ///< cluster kernel: the work outgrew one cluster; continue with the grid-wide kernel
+  near_far_shrank = 2      ///< grid-wide kernel: the near queue fits one cluster again
 };
 
 constexpr unsigned near_far_inf_bits = 0x7f800000u;
@@ -58,7 +67,10 @@ template <typename vertex_t, typename edge_t, typename weight_t, typename operat
 __global__ void __launch_bounds__(256, 2)
     near_far_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op, priority_t priority,
                     float delta, vertex_t* near0, vertex_t* near1, vertex_t* far0, vertex_t* far1, int* queue_stamp,
-                    int* far_flag, near_far_state_t* state, unsigned long long capacity, int max_levels) {
+                    int* far_flag, near_far_state_t* state, unsigned long long capacity, int max_levels,
+                    unsigned long long shrink_limit) {
+  // shrink_limit > 0: return (near_far_shrank) as soon as a near level has at most that many vertices, so the host
+  // can continue in near_far_cluster_kernel, whose level barrier is ~10x cheaper
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   volatile near_far_state_t* st = state;
@@ -68,7 +80,8 @@ __global__ void __launch_bounds__(256, 2)
   vertex_t* near_q[2] = {near0, near1};
   vertex_t* far_q[2] = {far0, far1};
   unsigned long long my_relax = 0;
-  int level = 0;
+  int level = st->level;
+  int reason = near_far_done;
   bool stop = false;
 
   while (!stop) {
@@ -78,6 +91,11 @@ __global__ void __launch_bounds__(256, 2)
       if (n_in == 0) break;
       if (level >= max_levels) {
         stop = true;
+        break;
+      }
+      if (n_in <= shrink_limit) {  // uniform: every thread read the same value after the barrier
+        stop = true;
+        reason = near_far_shrank;
         break;
       }
       const vertex_t* q_in = near_q[level & 1];
@@ -163,8 +181,12 @@ __global__ void __launch_bounds__(256, 2)
     }
     grid.sync();
     const float old_threshold = st->threshold;
-    float new_threshold = (floorf(__uint_as_float(st->far_min_bits) / delta) + 1.0f) * delta;
+    const float far_min = __uint_as_float(st->far_min_bits);
+    float new_threshold = (floorf(far_min / delta) + 1.0f) * delta;
     if (!(new_threshold > old_threshold)) new_threshold = old_threshold + delta;
+    // strict progress past the smallest pending key: both forms above can round to <= far_min once keys exceed
+    // ~2^24 * delta, and a far pile that never drains would spin this persistent kernel for ever
+    if (!(new_threshold > far_min)) new_threshold = nextafterf(far_min, __int_as_float(0x7f800000));
     {
       vertex_t* q_in = near_q[level & 1];  // promoted vertices become the input of the next near level
       unsigned long long* in_count = &state->near_count[level % 3];
@@ -199,7 +221,231 @@ __global__ void __launch_bounds__(256, 2)
 
   my_relax = b200::warp_sum(my_relax);
   if (lane == 0 && my_relax) atomicAdd(&state->relaxations, my_relax);
-  if (tid == 0) st->levels = level;
+  if (tid == 0) {
+    st->levels = level;
+    st->level = level;
+    st->exit_reason = reason;
+  }
+}
+
+/**
+ * @brief The same traversal run by ONE thread-block cluster (8 or 16 CTAs x 1024 threads on neighbouring SMs).
+ *
+ * Why. On the 4900 x 4900 grid a near level holds at most ~10 K vertices and there are ~12.6 K levels; the grid-wide
+ * kernel spends ~15 us per level, almost all of it in the 148-CTA cooperative barrier and in dependent L2 round
+ * trips on the queue counters. A cluster gives (a) a HARDWARE barrier (barrier.cluster, ~0.2 us instead of ~3 us),
+ * (b) the queue counters and the threshold in the leader CTA's shared memory, reached by the other CTAs through
+ * distributed shared memory (~215 cycles, atomics included) instead of L2 atomics, and 16 K threads are still one
+ * thread per relaxation at these frontier sizes. Queues, stamps and the user's data stay in global memory (L2).
+ * Appends are warp-aggregated (ballot + one DSMEM atomic per warp), so the leader's shared-memory port sees at most
+ * a few hundred atomics per level. When a level or the far pile outgrows `grow_limit` the kernel writes its state
+ * back and returns near_far_grew; execute_near_far continues with the grid-wide kernel.
+ */
+template <typename vertex_t, typename edge_t, typename weight_t, typename operator_t, typename priority_t>
+__global__ void __launch_bounds__(1024, 1)
+    near_far_cluster_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op, priority_t priority,
+                            float delta, vertex_t* near0, vertex_t* near1, vertex_t* far0, vertex_t* far1,
+                            int* queue_stamp, int* far_flag, near_far_state_t* state, unsigned long long capacity,
+                            int max_levels, unsigned long long grow_limit) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ near_far_state_t s_ctl;          // live copy; only the leader's is used
+  __shared__ unsigned long long s_in[4];      // per-CTA broadcast of the level's inputs
+  near_far_state_t* ctl = cluster.map_shared_rank(&s_ctl, 0);
+  const unsigned lane = b200::lane_id();
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long threads = (unsigned long long)gridDim.x * blockDim.x;
+  const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
+  vertex_t* near_q[2] = {near0, near1};
+  vertex_t* far_q[2] = {far0, far1};
+  if (leader) s_ctl = *state;
+  cluster.sync();
+  unsigned long long my_relax = 0;
+  int level = 0;
+  if (threadIdx.x == 0) s_in[0] = (unsigned long long)ctl->level;
+  __syncthreads();
+  level = int(s_in[0]);
+  int reason = near_far_done;
+  bool overflowed = false;
+
+  // warp-aggregated append to a queue whose length lives in distributed shared memory
+  auto append = [&](bool keep, vertex_t value, vertex_t* queue, unsigned long long* count) {
+    const unsigned votes = __ballot_sync(b200::full_mask, keep);
+    if (votes == 0) return;
+    const int first = __ffs(votes) - 1;
+    unsigned long long base = 0;
+    if (int(lane) == first) base = atomicAdd(count, (unsigned long long)__popc(votes));
+    base = __shfl_sync(b200::full_mask, base, first);
+    if (keep) {
+      const unsigned long long at = base + __popc(votes & b200::lanes_below(lane));
+      if (at < capacity) queue[at] = value; else overflowed = true;
+    }
+  };
+
+  for (;;) {
+    __syncthreads();  // s_in reuse
+    if (threadIdx.x == 0) {
+      s_in[0] = ctl->near_count[level % 3];
+      s_in[1] = (unsigned long long)__float_as_uint(ctl->threshold);
+      s_in[2] = (unsigned long long)ctl->far_selector;
+      s_in[3] = ctl->far_count[ctl->far_selector];
+    }
+    __syncthreads();
+    const unsigned long long n_in = s_in[0];
+    const float threshold = __uint_as_float(unsigned(s_in[1]));
+    const int fsel = int(s_in[2]);
+    const unsigned long long n_far = s_in[3];
+    if (n_in > 0) {
+      // ------------------------------ one near level, one cluster barrier ------------------------------
+      if (level >= max_levels) break;
+      if (n_in > grow_limit) {
+        reason = near_far_grew;
+        break;
+      }
+      const vertex_t* q_in = near_q[level & 1];
+      vertex_t* q_out = near_q[(level + 1) & 1];
+      unsigned long long* out_count = &ctl->near_count[(level + 1) % 3];
+      unsigned long long* far_count = &ctl->far_count[fsel];
+      vertex_t* far_out = far_q[fsel];
+      const int next_level = level + 1;
+      if (leader) s_ctl.near_count[(level + 2) % 3] = 0;  // read a level ago, appended to a level from now
+
+      auto route = [&](bool improved, vertex_t u) {  // called by all 32 lanes
+        bool to_near = false, to_far = false;
+        if (improved) {
+          if (float(priority(u)) < threshold)
+            to_near = atomicExch(queue_stamp + u, next_level) != next_level;
+          else
+            to_far = atomicExch(far_flag + u, 1) == 0;
+        }
+        append(to_near, u, q_out, out_count);
+        append(to_far, u, far_out, far_count);
+      };
+
+      for (unsigned long long base = (tid >> 5) << 5; base < n_in; base += threads) {
+        const unsigned long long i = base + lane;
+        vertex_t v = 0;
+        edge_t beg = 0, deg = 0;
+        if (i < n_in) {
+          v = q_in[i];
+          beg = A.offsets[v];
+          deg = A.offsets[v + 1] - beg;
+        }
+        unsigned long_lanes = __ballot_sync(b200::full_mask, deg >= 32);
+        while (long_lanes) {  // adjacency lists of >= 32 edges: the whole warp, coalesced
+          const int owner = __ffs(long_lanes) - 1;
+          long_lanes &= long_lanes - 1;
+          const vertex_t src = __shfl_sync(b200::full_mask, v, owner);
+          const edge_t b = __shfl_sync(b200::full_mask, beg, owner);
+          const edge_t e_end = b + __shfl_sync(b200::full_mask, deg, owner);
+          for (edge_t e0 = b; e0 < e_end; e0 += 32) {
+            const edge_t e = e0 + edge_t(lane);
+            bool improved = false;
+            vertex_t u = 0;
+            if (e < e_end) {
+              vertex_t s = src;
+              u = __ldg(A.indices + e);
+              edge_t edge = e;
+              weight_t w = A.values ? __ldg(A.values + e) : weight_t(1);
+              ++my_relax;
+              improved = op(s, u, edge, w);
+            }
+            route(improved, u);
+          }
+        }
+        const edge_t short_deg = deg < 32 ? deg : edge_t(0);
+        const edge_t trips = b200::warp_max(short_deg);  // warp-uniform trip count keeps the ballots converged
+        for (edge_t k = 0; k < trips; ++k) {
+          bool improved = false;
+          vertex_t u = 0;
+          if (k < short_deg) {
+            vertex_t s = v;
+            edge_t edge = beg + k;
+            u = __ldg(A.indices + edge);
+            weight_t w = A.values ? __ldg(A.values + edge) : weight_t(1);
+            ++my_relax;
+            improved = op(s, u, edge, w);
+          }
+          route(improved, u);
+        }
+      }
+      cluster.sync();
+      ++level;
+      continue;
+    }
+    // ------------------------------ far pile: raise the threshold, split ------------------------------
+    if (n_far == 0) break;
+    if (n_far > 4 * grow_limit) {
+      reason = near_far_grew;
+      break;
+    }
+    const vertex_t* far_in = far_q[fsel];
+    vertex_t* far_keep = far_q[fsel ^ 1];
+    {
+      unsigned lowest = near_far_inf_bits;
+      for (unsigned long long i = tid; i < n_far; i += threads) {
+        const unsigned bits = __float_as_uint(float(priority(far_in[i])));
+        lowest = bits < lowest ? bits : lowest;
+      }
+      for (int d = 16; d > 0; d >>= 1) {
+        const unsigned other = __shfl_xor_sync(b200::full_mask, lowest, d);
+        lowest = other < lowest ? other : lowest;
+      }
+      if (lane == 0 && lowest != near_far_inf_bits) atomicMin(&ctl->far_min_bits, lowest);
+    }
+    cluster.sync();
+    if (threadIdx.x == 0) s_in[0] = (unsigned long long)ctl->far_min_bits;
+    __syncthreads();
+    const float far_min = __uint_as_float(unsigned(s_in[0]));
+    const float old_threshold = threshold;
+    float new_threshold = (floorf(far_min / delta) + 1.0f) * delta;
+    if (!(new_threshold > old_threshold)) new_threshold = old_threshold + delta;
+    if (!(new_threshold > far_min)) new_threshold = nextafterf(far_min, __int_as_float(0x7f800000));
+    {
+      vertex_t* q_in = near_q[level & 1];  // promoted vertices become the input of the next near level
+      unsigned long long* in_count = &ctl->near_count[level % 3];
+      unsigned long long* keep_count = &ctl->far_count[fsel ^ 1];
+      for (unsigned long long base = (tid >> 5) << 5; base < n_far; base += threads) {
+        const unsigned long long i = base + lane;
+        bool promote = false, keep = false;
+        vertex_t u = 0;
+        if (i < n_far) {
+          u = far_in[i];
+          const float p = float(priority(u));
+          if (p < old_threshold) {
+            far_flag[u] = 0;  // stale: it was expanded from `near` when it dropped below the old threshold
+          } else if (p < new_threshold) {
+            far_flag[u] = 0;
+            promote = atomicExch(queue_stamp + u, level) != level;
+          } else {
+            keep = true;
+          }
+        }
+        append(promote, u, q_in, in_count);
+        append(keep, u, far_keep, keep_count);
+      }
+    }
+    cluster.sync();
+    if (leader) {
+      s_ctl.threshold = new_threshold;
+      s_ctl.far_count[fsel] = 0;
+      s_ctl.far_selector = fsel ^ 1;
+      s_ctl.far_min_bits = near_far_inf_bits;
+      s_ctl.splits = s_ctl.splits + 1;
+    }
+    cluster.sync();
+  }
+
+  my_relax = b200::warp_sum(my_relax);
+  if (lane == 0 && my_relax) atomicAdd(&ctl->relaxations, my_relax);
+  if (__syncthreads_or(overflowed) && threadIdx.x == 0) ctl->overflow = 1;
+  cluster.sync();
+  if (leader) {
+    s_ctl.levels = level;
+    s_ctl.level = level;
+    s_ctl.exit_reason = reason;
+    *state = s_ctl;
+  }
 }
 
 }  // namespace kernels
@@ -208,6 +454,12 @@ __global__ void __launch_bounds__(256, 2)
 inline int& near_far_ctas_per_sm() {
   static int ctas = 1;  // measured on the 4900^2 grid: 1 CTA/SM 178 ms, 2: 192 ms, 4: 232 ms (barrier cost)
   return ctas;
+}
+
+/// Development knob (ess_tune "near_far_cluster"): run small levels in one thread-block cluster (default on).
+inline int& near_far_cluster_enabled() {
+  static int enabled = 1;
+  return enabled;
 }
 
 /// Statistics of one execute_near_far call.
@@ -255,25 +507,80 @@ near_far_result_t execute_near_far(graph_t& G, enactor_type* E, operator_t op, p
   h.far_min_bits = kernels::near_far_inf_bits;
   cudaMemcpyAsync(state.data(), &h, sizeof(h), cudaMemcpyHostToDevice, stream);
 
-  auto kernel = kernels::near_far_kernel<vertex_t, edge_t, weight_t, operator_t, priority_t>;
+  auto grid_kernel = kernels::near_far_kernel<vertex_t, edge_t, weight_t, operator_t, priority_t>;
+  auto cluster_kernel = kernels::near_far_cluster_kernel<vertex_t, edge_t, weight_t, operator_t, priority_t>;
   int per_sm = 0;
-  error::throw_if_exception(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0), "occupancy");
+  error::throw_if_exception(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_kernel, 256, 0), "occupancy");
   error::throw_if_exception(per_sm < 1, "execute_near_far: kernel does not fit on an SM");
   const int want = near_far_ctas_per_sm();
   const unsigned grid = unsigned(ctx->sm_count()) * unsigned(per_sm < want ? per_sm : want);
+  // one cluster of 16 CTAs (non-portable size) when the device schedules it, else 8; 0 = no cluster path
+  int cluster_ctas = 0;
+  if (near_far_cluster_enabled()) {
+    for (int size : {16, 8}) {
+      cudaLaunchConfig_t probe{};
+      probe.gridDim = dim3(unsigned(size));
+      probe.blockDim = dim3(1024);
+      cudaLaunchAttribute attr{};
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = unsigned(size);
+      attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+      probe.attrs = &attr;
+      probe.numAttrs = 1;
+      if (size > 8 && cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+                          cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+      int clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&clusters, cluster_kernel, &probe) == cudaSuccess && clusters >= 1) {
+        cluster_ctas = size;
+        break;
+      }
+      cudaGetLastError();
+    }
+  }
+  const unsigned long long grow_limit = 4ull * 1024ull * unsigned(cluster_ctas);   // cluster -> grid above this
+  const unsigned long long shrink_limit = cluster_ctas ? grow_limit / 4 : 0ull;    // grid -> cluster at or below this
   auto adjacency = A;
   vertex_t *near0 = in->data(), *near1 = out->data(), *f0 = far0.data(), *f1 = far1.data();
   int *stamp_ptr = stamp.data(), *flag_ptr = far_flag.data();
   near_far_state_t* state_ptr = state.data();
   unsigned long long capacity = n;
-  void* args[] = {&adjacency, &op,   &priority, &delta,     &near0,    &near1,
-                  &f0,        &f1,   &stamp_ptr, &flag_ptr, &state_ptr, &capacity, &max_levels};
+  bool use_cluster = cluster_ctas > 0 && nf <= grow_limit;
   ctx->profiler().begin(gcuda::profiler_t::push_expand, stream);
-  error::throw_if_exception(cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(256), args, 0, stream),
-                            "execute_near_far launch");
-  ctx->profiler().end(stream);
-  cudaMemcpyAsync(&h, state.data(), sizeof(h), cudaMemcpyDeviceToHost, stream);
-  ctx->synchronize();
+  int launches = 0;
+  for (;;) {
+    if (use_cluster) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(unsigned(cluster_ctas));
+      cfg.blockDim = dim3(1024);
+      cfg.stream = stream;
+      cudaLaunchAttribute attr{};
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = unsigned(cluster_ctas);
+      attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      error::throw_if_exception(cudaLaunchKernelEx(&cfg, cluster_kernel, adjacency, op, priority, delta, near0, near1,
+                                                   f0, f1, stamp_ptr, flag_ptr, state_ptr, capacity, max_levels,
+                                                   grow_limit),
+                                "execute_near_far cluster launch");
+    } else {
+      unsigned long long limit = shrink_limit;
+      void* args[] = {&adjacency, &op,   &priority,  &delta,    &near0,     &near1,    &f0,
+                      &f1,        &stamp_ptr, &flag_ptr, &state_ptr, &capacity, &max_levels, &limit};
+      error::throw_if_exception(
+          cudaLaunchCooperativeKernel((void*)grid_kernel, dim3(grid), dim3(256), args, 0, stream),
+          "execute_near_far launch");
+    }
+    ++launches;
+    cudaMemcpyAsync(&h, state.data(), sizeof(h), cudaMemcpyDeviceToHost, stream);
+    ctx->synchronize();
+    if (h.overflow != 0 || h.exit_reason == kernels::near_far_done) break;
+    use_cluster = h.exit_reason == kernels::near_far_shrank;
+  }
+  ctx->profiler().end(stream, launches);
   error::throw_if_exception(h.overflow != 0, "execute_near_far: queue overflow");
   in->set_number_of_elements(0);
   out->set_number_of_elements(0);

@@ -31,6 +31,11 @@ namespace kernels {
 using b200::counter_t;
 using gcuda::scratch_t;
 
+/// Hint encoding (graph::build::pull_hints): head[v] >= 0 = highest-degree in-neighbour of v; -1 = v has no
+/// in-edges; <= -2 = v has exactly ONE in-edge, from vertex -2 - head[v] (nothing to walk when that hint misses).
+template <typename vertex_t>
+__device__ __forceinline__ vertex_t hint_vertex(vertex_t h) { return h < -1 ? vertex_t(-2) - h : h; }
+
 /// visited := {isolated vertices} ∪ frontier; also Σdeg(frontier) -> counters[aux2].
 template <typename vertex_t, typename edge_t>
 __global__ void __launch_bounds__(256)
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(256, 6)
       const unsigned v = (w << 5) + lane;
       s.beg = A.offsets[v];
       s.end = A.offsets[v + 1];
-      if (hinted) s.head = __ldg(A.head + v);
+      if (hinted) s.head = hint_vertex(__ldg(A.head + v));
     }
     return s;
   };
@@ -181,49 +186,56 @@ __global__ void __launch_bounds__(256, 6)
   }
 }
 
-/// Shared-memory footprint of pull_chunk_kernel: one miss queue per warp. A chunk is 32 words = 1024 vertices; the
-/// queue holds every miss of one chunk plus the < 32 left over from the previous drain.
+/// A chunk is 32 words = 1024 vertices: what one warp takes per trip of pull_chunk_kernel.
 constexpr int pull_chunk_words = 32;
-constexpr int pull_queue_cap = pull_chunk_words * 32 + 32;
-constexpr int pull_long_list = 64;  ///< adjacency lists longer than this are walked by the whole warp
+constexpr int pull_queue_cap = 32 + 4 * 32;  ///< walk queue of a warp: < 32 left over + one 4-batch group of misses
+constexpr int pull_long_list = 64;           ///< adjacency lists longer than this are walked by the whole warp
 
 /**
  * @brief One bottom-up level, second design (same contract as pull_step_kernel minus the Σdeg of the next
  * frontier: counters[out_count] += |next frontier|, counters[aux0] += unvisited vertices probed,
- * counters[aux1] += in-edges read).
+ * counters[aux1] += in-edges read, counters[aux2] += vertices whose adjacency was walked).
  *
  * Why a second design. ncu on pull_step_kernel (profiles/r01c_pull_step_summary.txt): 223 warp instructions per
  * 32-vertex word at 12-17 active lanes per instruction, DRAM traffic 3.1x the algorithmic bytes. A CPU model of the
- * same levels (scale-20 Kronecker) shows why: the head hint resolves 82-99 % of the probed vertices, and the ones it
- * does not resolve are almost all degree-1/2 vertices whose single neighbour is not in the frontier — so the warp
- * spent most of its instructions in a walk loop that 2-5 of its 32 lanes were executing, and it paid the row
- * bounds (2 x sizeof(edge_t) per vertex, coalesced) for every probed vertex although only the misses need them.
- *   phase 1 (hint): a warp takes a chunk of 32 words; lane L loads visited word L (one coalesced 128-byte access),
- *     then the chunk's words are processed four at a time: 4 coalesced head loads -> 4 frontier-bit probes ->
- *     operator (owner-exclusive form) -> ballot. No row bounds are read. Lanes whose hint missed push their vertex
- *     into the warp's shared-memory queue (ballot + popc, no atomics).
- *   phase 2 (walk): after the chunk's words are written back, the queue is drained 32 vertices at a time with ALL
- *     lanes busy: row bounds on demand, the list walked until the operator returns true. Lists longer than
- *     pull_long_list are left to a warp-cooperative pass (coalesced 32-edge strides, ballot, first hit in list
- *     order). Vertices found here are ORed into the (already written) next/visited words.
+ * same levels (Kronecker scale 20-22) shows why: the head hint resolves 76-99 % of the probed vertices, and 56-99 %
+ * of the vertices it does not resolve have a single in-edge — the hint WAS their whole adjacency — so the warp
+ * spent most of its instructions in a walk loop that 2-5 of its 32 lanes were executing, re-reading a neighbour it
+ * already knew, and it paid the row bounds (2 x sizeof(edge_t), one random sector) for every probed vertex although
+ * only real walks need them.
+ *   compaction: a warp takes a chunk of 32 words; lane L loads visited word L (one coalesced 128-byte access) and
+ *     the chunk's unvisited vertices are compacted into shared memory (shuffle scan of the popcounts), so every
+ *     later instruction runs with 32 busy lanes however sparse the level is.
+ *   hint phase: the compacted vertices are taken 4 x 32 at a time: 4 head loads -> 4 frontier-word probes ->
+ *     operator (owner-exclusive form); found bits are ORed into the chunk's 32 result words in shared memory. No row
+ *     bounds are read. Single-in-edge vertices whose hint missed are finished. The others join the walk queue.
+ *   walk: whenever 32 vertices are queued they are walked one per lane, all lanes busy: row bounds on demand, the
+ *     list read until the operator returns true. Lists longer than pull_long_list are left to a warp-cooperative
+ *     pass (coalesced 32-edge strides, ballot, candidates offered in list order).
+ *   write-back: next/visited words of the chunk leave shared memory as one coalesced store each.
  * Semantics: hinted in-neighbour first, then the in-edges in list order, until the operator returns true — as
  * pull_step_kernel. Single-GPU form (A holds every row; visited/next are full-length).
  */
 template <typename vertex_t, typename edge_t, typename weight_t, typename operator_t>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 5)
     pull_chunk_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op,
                       const unsigned* __restrict__ frontier_bits, unsigned* __restrict__ next_bits,
                       unsigned* __restrict__ visited, counter_t* counters) {
+  __shared__ unsigned short s_open[8][pull_chunk_words * 32];
   __shared__ unsigned s_queue[8][pull_queue_cap];
+  __shared__ unsigned s_fresh[8][pull_chunk_words];
   const unsigned lane = b200::lane_id();
+  unsigned short* open_list = s_open[b200::warp_id()];
   unsigned* queue = s_queue[b200::warp_id()];
+  unsigned* fresh_words = s_fresh[b200::warp_id()];
   const unsigned n = unsigned(A.n);
   const unsigned n_words = (n + 31u) >> 5;
   const unsigned n_chunks = (n_words + pull_chunk_words - 1) / pull_chunk_words;
   const unsigned warps = (gridDim.x * blockDim.x) >> 5;
   const bool hinted = A.head != nullptr;
-  unsigned found_vertices = 0, scanned = 0, inspected = 0;
-  unsigned queued = 0;  // warp-uniform
+  unsigned found_vertices = 0, scanned = 0, inspected = 0, walked = 0;
+  unsigned queued = 0;                    // warp-uniform
+  unsigned live_chunk = 0xffffffffu;      // chunk whose result words are still in shared memory
   constexpr unsigned tried_flag = 0x80000000u;  // queue entry: the hint was offered to the operator and refused
 
   // walks the adjacency of up to 32 queued vertices (one per lane), all lanes busy
@@ -238,8 +250,9 @@ __global__ void __launch_bounds__(256, 4)
     if (mine) {
       beg = A.offsets[v];
       end = A.offsets[v + 1];
+      ++walked;
     }
-    const vertex_t head = (mine && head_tried) ? __ldg(A.head + v) : vertex_t(-1);
+    const vertex_t head = (mine && head_tried) ? hint_vertex(__ldg(A.head + v)) : vertex_t(-1);
     bool found = false;
     const bool is_long = mine && (end - beg) > edge_t(pull_long_list);
     if (mine && !is_long) {
@@ -288,75 +301,95 @@ __global__ void __launch_bounds__(256, 4)
     }
     if (found) {
       const unsigned bit = 1u << (unsigned(v) & 31u);
-      atomicOr(next_bits + (unsigned(v) >> 5), bit);
-      atomicOr(visited + (unsigned(v) >> 5), bit);
-      ++found_vertices;
+      if ((unsigned(v) >> 10) == live_chunk) {  // result words of this chunk are still in shared memory
+        atomicOr(fresh_words + ((unsigned(v) >> 5) & 31u), bit);
+      } else {  // older chunk: its words were written back; OR into them
+        atomicOr(next_bits + (unsigned(v) >> 5), bit);
+        atomicOr(visited + (unsigned(v) >> 5), bit);
+        ++found_vertices;
+      }
     }
+    __syncwarp();
   };
 
   for (unsigned chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < n_chunks; chunk += warps) {
     const unsigned w_mine = chunk * pull_chunk_words + lane;
     const unsigned seen_mine = w_mine < n_words ? visited[w_mine] : 0xffffffffu;
-    unsigned fresh_mine = 0;
-    // groups of 4 consecutive words with at least one unvisited vertex
-    unsigned open_words = __ballot_sync(b200::full_mask, seen_mine != 0xffffffffu);
-#pragma unroll 1
-    for (int g = 0; g < pull_chunk_words / 4; ++g) {
-      if (!((open_words >> (4 * g)) & 0xfu)) continue;  // warp-uniform
-      unsigned seen[4];
-      vertex_t head[4];
+    fresh_words[lane] = 0u;
+    live_chunk = chunk;
+    // compact the chunk's unvisited vertices (ascending) into shared memory
+    unsigned open_bits = ~seen_mine;
+    const unsigned mine_open = __popc(open_bits);
+    const unsigned incl = b200::warp_inclusive_sum(mine_open);
+    const unsigned total = __shfl_sync(b200::full_mask, incl, 31);
+    {
+      unsigned at = incl - mine_open;
+      while (open_bits) {
+        const unsigned b = __ffs(open_bits) - 1;
+        open_bits &= open_bits - 1;
+        open_list[at++] = (unsigned short)((lane << 5) | b);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) scanned += total;
+    for (unsigned base = 0; base < total; base += 128) {
+      unsigned loc[4];
+      vertex_t hid[4];
+      bool single[4];
       unsigned probe[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        seen[k] = __shfl_sync(b200::full_mask, seen_mine, 4 * g + k);
-        head[k] = vertex_t(-1);
-        if (!((seen[k] >> lane) & 1u)) {
-          const unsigned v = ((chunk * pull_chunk_words + 4 * g + k) << 5) + lane;
-          if (hinted) head[k] = __ldg(A.head + v);
-        }
+        const unsigned idx = base + 32u * k + lane;
+        loc[k] = idx < total ? unsigned(open_list[idx]) : 0xffffffffu;
+        vertex_t h = vertex_t(-1);
+        if (loc[k] != 0xffffffffu && hinted) h = __ldg(A.head + ((chunk << 10) + loc[k]));
+        single[k] = h < vertex_t(-1);
+        hid[k] = hint_vertex(h);
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) probe[k] = head[k] >= 0 ? __ldg(frontier_bits + (unsigned(head[k]) >> 5)) : 0u;
+      for (int k = 0; k < 4; ++k) probe[k] = hid[k] >= 0 ? __ldg(frontier_bits + (unsigned(hid[k]) >> 5)) : 0u;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const bool open = !((seen[k] >> lane) & 1u);
-        const vertex_t v = vertex_t(((chunk * pull_chunk_words + 4 * g + k) << 5) + lane);
+        const bool valid = loc[k] != 0xffffffffu;
+        const vertex_t v = vertex_t((chunk << 10) + (valid ? loc[k] : 0u));
         bool found = false, tried = false;
-        if (open) {
-          ++scanned;
-          if (head[k] >= 0 && ((probe[k] >> (unsigned(head[k]) & 31u)) & 1u)) {
-            const edge_t edge = __ldg(A.head_edge + v);
-            const weight_t weight = A.values ? __ldg(A.values + edge) : weight_t(1);
-            found = call_pull(op, head[k], v, edge, weight);
-            tried = true;
-          }
+        if (valid && hid[k] >= 0 && ((probe[k] >> (unsigned(hid[k]) & 31u)) & 1u)) {
+          const edge_t edge = __ldg(A.head_edge + v);
+          const weight_t weight = A.values ? __ldg(A.values + edge) : weight_t(1);
+          found = call_pull(op, hid[k], v, edge, weight);
+          tried = true;
         }
-        const unsigned fresh = __ballot_sync(b200::full_mask, found);
-        if (int(lane) == 4 * g + k) fresh_mine = fresh;
-        const bool miss = open && !found;
+        if (found) atomicOr(fresh_words + (loc[k] >> 5), 1u << (loc[k] & 31u));
+        // a vertex with a single in-edge has nothing left to offer once its hint missed or was refused
+        const bool miss = valid && !found && !(single[k] && hinted);
         const unsigned misses = __ballot_sync(b200::full_mask, miss);
         if (miss) queue[queued + __popc(misses & b200::lanes_below(lane))] = unsigned(v) | (tried ? tried_flag : 0u);
         queued += __popc(misses);
       }
+      __syncwarp();
+      while (queued >= 32) drain(32);
     }
+    __syncwarp();
+    const unsigned fresh_mine = fresh_words[lane];
     if (w_mine < n_words) {
       next_bits[w_mine] = fresh_mine;
       if (fresh_mine) visited[w_mine] = seen_mine | fresh_mine;
     }
     found_vertices += __popc(fresh_mine);
-    __syncwarp();  // queue writes and the word stores above precede the drain's reads / atomics
-    while (queued >= 32) drain(32);
+    live_chunk = 0xffffffffu;
+    __syncwarp();  // the word stores above precede the atomics of later drains on the same words
   }
-  __syncwarp();
   if (queued) drain(queued);
 
   found_vertices = b200::warp_sum(found_vertices);
   scanned = b200::warp_sum(scanned);
   inspected = b200::warp_sum(inspected);
+  walked = b200::warp_sum(walked);
   if (lane == 0) {
     if (found_vertices) atomicAdd(counters + scratch_t::out_count, counter_t(found_vertices));
     if (scanned) atomicAdd(counters + scratch_t::aux0, counter_t(scanned));
     if (inspected) atomicAdd(counters + scratch_t::aux1, counter_t(inspected));
+    if (walked) atomicAdd(counters + scratch_t::aux2, counter_t(walked));  // vertices whose adjacency was walked
   }
 }
 

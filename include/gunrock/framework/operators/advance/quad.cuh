@@ -163,9 +163,9 @@ __device__ __forceinline__ unsigned visit_items(const graph::adjacency_t<vertex_
 #pragma unroll
       for (int i = 0; i < N; ++i)
         if (claimed & (1u << i)) {
-          const edge_t lo = A.offsets[nbr[i]], hi = A.offsets[nbr[i] + 1];  // issued before the operator's store
           if (call_pull(op, src[i >> 2], nbr[i], edge_t(e0[i >> 2] + (i & 3)), wt[i])) keep |= 1u << i;
-          fresh_edges += counter_t(hi - lo);
+          if constexpr (count_fresh_edges_in_kernel)
+            fresh_edges += counter_t(A.offsets[nbr[i] + 1] - A.offsets[nbr[i]]);
         }
     }
   } else {
@@ -190,7 +190,8 @@ __device__ __forceinline__ unsigned visit_items(const graph::adjacency_t<vertex_
           if (k) {
             const unsigned bit = 1u << (unsigned(d) & 31u);
             k = !(atomicOr(&visited[unsigned(d) >> 5], bit) & bit);
-            if (k) fresh_edges += counter_t(A.offsets[d + 1] - A.offsets[d]);
+            if constexpr (count_fresh_edges_in_kernel)
+              if (k) fresh_edges += counter_t(A.offsets[d + 1] - A.offsets[d]);
           }
         }
         if constexpr (policy == visit_t::unique_output) {
@@ -706,10 +707,12 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
 }
 
 /**
- * @brief Grid-wide expansion of the deferred hubs. Each hub's quad range is cut into 512-quad tiles; CTA b takes
- * tiles b, b + grid, ... of every hub. The tile's 8 KB of column indices are brought into shared memory by ONE
- * cp.async.bulk issued by thread 0 (double buffered: tile k+1 is in flight while tile k is expanded), consumers
- * wait on the stage's mbarrier and read their two quads with 128-bit shared loads.
+ * @brief Grid-wide expansion of the deferred hubs. Each hub's quad range is cut into 512-quad tiles; the tiles of
+ * all hubs form one global sequence that is dealt round-robin to the CTAs (tile g -> CTA g mod grid), so the grid
+ * stays balanced whatever the degree mix. Hubs are taken 256 at a time: their bounds are loaded by the CTA in
+ * parallel and scanned into tile prefixes in shared memory. A tile's 8 KB of column indices are brought into shared
+ * memory by ONE cp.async.bulk issued by thread 0 (double buffered: tile k+1 is in flight while tile k is expanded),
+ * consumers wait on the stage's mbarrier and read their two quads with 128-bit shared loads.
  */
 template <bool has_output, visit_t policy, typename vertex_t, typename edge_t, typename weight_t, typename operator_t>
 __global__ void __launch_bounds__(cta_threads, 4)
@@ -721,6 +724,10 @@ __global__ void __launch_bounds__(cta_threads, 4)
   __shared__ __align__(128) vertex_t s_col[2][bulk_tile_quads * 4];
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ warp_stage_t<vertex_t> stages[has_output ? quad_warps : 1];
+  __shared__ vertex_t s_v[cta_threads];
+  __shared__ edge_t s_beg[cta_threads], s_end[cta_threads];
+  __shared__ unsigned long long s_first[cta_threads + 1];  // first global tile of each hub of the batch
+  __shared__ unsigned long long s_scan[cta_threads / 32 + 1];
   if constexpr (has_output)
     if (!output_fits(counters, capacity)) return;
   const std::size_t count = std::size_t(*size_ptr);
@@ -743,87 +750,99 @@ __global__ void __launch_bounds__(cta_threads, 4)
     int n_quads;        // quads in the tile (<= 512)
     int covered;        // elements of the tile delivered by the bulk copy (the array's ragged last quad is not)
   };
-  // cursor over this CTA's tiles: (item, t) with t = blockIdx.x, blockIdx.x + gridDim.x, ... inside each item
-  std::size_t item = 0;
-  long long t = blockIdx.x;
-  vertex_t cv = 0;
-  edge_t cbeg = 0, cend = 0;
-  long long item_quads = 0;
-  auto load_item = [&]() {
-    cv = big_list[item];
-    cbeg = A.offsets[cv];
-    cend = A.offsets[cv + 1];
-    item_quads = cend > cbeg ? (long long)(((cend - 1) >> 2) - (cbeg >> 2) + 1) : 0;
-  };
-  auto seek = [&](tile_t& out) -> bool {
-    while (item < count) {
-      if (t * bulk_tile_quads < item_quads) {
-        out.v = cv, out.beg = cbeg, out.end = cend;
-        out.q_first = (cbeg >> 2) + edge_t(t * bulk_tile_quads);
-        const long long left = item_quads - t * bulk_tile_quads;
-        out.n_quads = int(left < bulk_tile_quads ? left : bulk_tile_quads);
-        const long long e_first = (long long)out.q_first * 4;
-        long long avail = (long long)A.m - e_first;  // elements of the array from the tile's start
-        avail &= ~3ll;
-        const long long want = (long long)out.n_quads * 4;
-        out.covered = int(want < avail ? want : avail);
-        return true;
-      }
-      ++item;
-      t = blockIdx.x;
-      if (item < count) load_item();
-    }
-    return false;
-  };
-  auto issue = [&](const tile_t& tile, int stage) {  // thread 0 only
-    const unsigned bytes = unsigned(tile.covered) * 4u;
-    mbarrier_arrive_expect_tx(&s_bar[stage], bytes);
-    if (bytes) bulk_copy_g2s(&s_col[stage][0], A.indices + (long long)tile.q_first * 4, bytes, &s_bar[stage]);
-  };
-
-  load_item();
-  tile_t cur, nxt;
-  bool have_cur = seek(cur);
-  if (have_cur && threadIdx.x == 0) issue(cur, 0);
-  int stage = 0;
   unsigned parity[2] = {0u, 0u};
-  while (have_cur) {
-    t += gridDim.x;
-    const bool have_nxt = seek(nxt);
-    if (have_nxt && threadIdx.x == 0) issue(nxt, stage ^ 1);
-    mbarrier_wait(&s_bar[stage], parity[stage]);
-    parity[stage] ^= 1u;
-
-    vertex_t src[quads_per_lane];
-    edge_t e0[quads_per_lane], lo[quads_per_lane], hi[quads_per_lane];
-    unsigned have = 0;
-    vertex_t nbr[round_items];
-#pragma unroll
-    for (int q = 0; q < quads_per_lane; ++q) {
-      const int k = q * cta_threads + int(threadIdx.x);  // thread-consecutive quads: conflict-free 128-bit LDS
-      src[q] = cur.v, lo[q] = cur.beg, hi[q] = cur.end;
-      e0[q] = (cur.q_first + edge_t(k)) * 4;
-      vertex_t c[4] = {0, 0, 0, 0};
-      if (k < cur.n_quads) {
-        have |= 1u << q;
-        if (4 * k + 4 <= cur.covered) {
-          const int4 x = *reinterpret_cast<const int4*>(&s_col[stage][4 * k]);
-          c[0] = vertex_t(x.x), c[1] = vertex_t(x.y), c[2] = vertex_t(x.z), c[3] = vertex_t(x.w);
-        } else {
-          load_quad(A.indices, e0[q], A.m, c);  // ragged last quad of the array
-        }
+  unsigned long long tiles_before = 0;  // global tiles of the batches already done
+  for (std::size_t batch = 0; batch < count; batch += cta_threads) {
+    const int in_batch = int(count - batch < std::size_t(cta_threads) ? count - batch : std::size_t(cta_threads));
+    {  // hubs of the batch: bounds in parallel, tile counts scanned
+      vertex_t v = 0;
+      edge_t b = 0, e = 0;
+      if (int(threadIdx.x) < in_batch) {
+        v = big_list[batch + threadIdx.x];
+        b = A.offsets[v];
+        e = A.offsets[v + 1];
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) nbr[4 * q + i] = c[i];
+      const unsigned long long nq = e > b ? (unsigned long long)(((e - 1) >> 2) - (b >> 2) + 1) : 0ull;
+      const unsigned long long tiles = (nq + bulk_tile_quads - 1) / bulk_tile_quads;
+      unsigned long long batch_tiles;
+      const unsigned long long before = b200::cta_exclusive_sum<cta_threads, unsigned long long>(tiles, batch_tiles, s_scan);
+      s_v[threadIdx.x] = v;
+      s_beg[threadIdx.x] = b;
+      s_end[threadIdx.x] = e;
+      s_first[threadIdx.x] = tiles_before + before;
+      if (threadIdx.x == cta_threads - 1) s_first[cta_threads] = tiles_before + batch_tiles;
     }
-    const unsigned live = live_mask<quads_per_lane>(have, e0, lo, hi);
-    const unsigned keep = visit_items<policy, quads_per_lane>(A, op, nbr, live, src, e0, visited, fresh_edges);
-    if constexpr (has_output)
-      stage_append<stage_cap>(nbr, keep, sbuf, staged, output, counters + scratch_t::out_count, capacity);
-    __syncthreads();  // everyone is done with s_col[stage] before it is refilled two tiles from now
-    cur = nxt;
-    have_cur = have_nxt;
-    stage ^= 1;
+    __syncthreads();
+    const unsigned long long batch_end = s_first[cta_threads];
+    // this CTA's tiles of the batch: g = first id >= tiles_before congruent to blockIdx.x, then += gridDim.x
+    unsigned long long g = tiles_before + (blockIdx.x + gridDim.x - unsigned(tiles_before % gridDim.x)) % gridDim.x;
+    auto describe = [&](unsigned long long id, tile_t& out) {
+      const int i = b200::upper_segment(s_first, cta_threads, id);  // hub of the batch owning tile `id`
+      const long long t = (long long)(id - s_first[i]);
+      out.v = s_v[i], out.beg = s_beg[i], out.end = s_end[i];
+      const long long item_quads = (long long)(((out.end - 1) >> 2) - (out.beg >> 2) + 1);
+      out.q_first = (out.beg >> 2) + edge_t(t * bulk_tile_quads);
+      const long long left = item_quads - t * bulk_tile_quads;
+      out.n_quads = int(left < bulk_tile_quads ? left : bulk_tile_quads);
+      long long avail = ((long long)A.m - (long long)out.q_first * 4) & ~3ll;  // whole quads left in the array
+      const long long want = (long long)out.n_quads * 4;
+      out.covered = int(want < avail ? want : avail);
+    };
+    auto issue = [&](const tile_t& tile, int stage) {  // thread 0 only
+      const unsigned bytes = unsigned(tile.covered) * 4u;
+      mbarrier_arrive_expect_tx(&s_bar[stage], bytes);
+      if (bytes) bulk_copy_g2s(&s_col[stage][0], A.indices + (long long)tile.q_first * 4, bytes, &s_bar[stage]);
+    };
+    tile_t cur, nxt;
+    bool have_cur = g < batch_end;
+    int stage = 0;
+    if (have_cur) {
+      describe(g, cur);
+      if (threadIdx.x == 0) issue(cur, 0);
+    }
+    while (have_cur) {
+      g += gridDim.x;
+      const bool have_nxt = g < batch_end;
+      if (have_nxt) {
+        describe(g, nxt);
+        if (threadIdx.x == 0) issue(nxt, stage ^ 1);
+      }
+      mbarrier_wait(&s_bar[stage], parity[stage]);
+      parity[stage] ^= 1u;
+
+      vertex_t src[quads_per_lane];
+      edge_t e0[quads_per_lane], lo[quads_per_lane], hi[quads_per_lane];
+      unsigned have = 0;
+      vertex_t nbr[round_items];
+#pragma unroll
+      for (int q = 0; q < quads_per_lane; ++q) {
+        const int k = q * cta_threads + int(threadIdx.x);  // thread-consecutive quads: conflict-free 128-bit LDS
+        src[q] = cur.v, lo[q] = cur.beg, hi[q] = cur.end;
+        e0[q] = (cur.q_first + edge_t(k)) * 4;
+        vertex_t c[4] = {0, 0, 0, 0};
+        if (k < cur.n_quads) {
+          have |= 1u << q;
+          if (4 * k + 4 <= cur.covered) {
+            const int4 x = *reinterpret_cast<const int4*>(&s_col[stage][4 * k]);
+            c[0] = vertex_t(x.x), c[1] = vertex_t(x.y), c[2] = vertex_t(x.z), c[3] = vertex_t(x.w);
+          } else {
+            load_quad(A.indices, e0[q], A.m, c);  // ragged last quad of the array
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nbr[4 * q + i] = c[i];
+      }
+      const unsigned live = live_mask<quads_per_lane>(have, e0, lo, hi);
+      const unsigned keep = visit_items<policy, quads_per_lane>(A, op, nbr, live, src, e0, visited, fresh_edges);
+      if constexpr (has_output)
+        stage_append<stage_cap>(nbr, keep, sbuf, staged, output, counters + scratch_t::out_count, capacity);
+      __syncthreads();  // everyone is done with s_col[stage] before it is refilled two tiles from now
+      cur = nxt;
+      have_cur = have_nxt;
+      stage ^= 1;
+    }
+    tiles_before = batch_end;
+    __syncthreads();  // batch tables are rewritten by the next iteration
   }
   if constexpr (has_output) stage_flush(sbuf, staged, output, counters + scratch_t::out_count, capacity);
   flush_fresh_edges<policy>(fresh_edges, counters);

@@ -25,8 +25,11 @@ void execute(frontier_t* input, frontier_t* output, std::size_t universe, gcuda:
   using vertex_t = typename frontier_t::vertex_type;
   using edge_t = typename frontier_t::edge_type;
   auto* ctx = context.get_context(0);
+  // sized on the context's (non-blocking) stream: a clear on the legacy default stream would not be ordered with
+  // the scatter convert() enqueues and could wipe bits that were just set
   frontier::frontier_t<vertex_t, edge_t, frontier::frontier_kind_t::vertex_frontier, frontier::frontier_view_t::bitmap>
-      dense(universe);
+      dense;
+  dense.resize(universe, ctx->stream());
   frontier::convert(*input, dense, ctx->stream());
   frontier::convert(dense, *output, *ctx);
 }

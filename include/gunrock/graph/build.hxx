@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256)
 }
 
 /// head[v] = in-neighbour of v with the largest degree (ties: first in the list), head_edge[v] = that in-edge;
-/// head[v] = -1 for vertices without in-edges. `degree_offsets` is the offsets array degrees are read from
+/// head[v] = -1 for vertices without in-edges, and -2 - u for vertices whose single in-edge comes from u. `degree_offsets` is the offsets array degrees are read from
 /// (the CSR when present, so "degree" is the out-degree of the in-neighbour). One warp per vertex.
 template <typename vertex_t, typename edge_t>
 __global__ void __launch_bounds__(256)
@@ -134,7 +134,13 @@ __global__ void __launch_bounds__(256)
       }
     }
     if (lane == 0) {
-      head[v] = best_deg >= 0 ? in_indices[best_edge] : vertex_t(-1);
+      // >= 0: the hint; -1: no in-edges; <= -2: the ONLY in-neighbour is -2 - head[v] (nothing to walk on a miss)
+      vertex_t h = vertex_t(-1);
+      if (best_deg >= 0) {
+        h = in_indices[best_edge];
+        if (e - b == 1) h = vertex_t(-2) - h;
+      }
+      head[v] = h;
       head_edge[v] = best_deg >= 0 ? best_edge : edge_t(-1);
     }
   }

@@ -231,6 +231,46 @@ def ref_bfs(off, col, src: int, return_ms=False):
     return (d, ms) if return_ms else d
 
 
+class RefGraph:
+    """The reference's csr_t built once; bfs()/sssp() call the reference's bfs_cpu::run / sssp_cpu::run on it.
+    The calls release the GIL (ctypes), so a thread pool runs several sources at once (bench.py's reference arm)."""
+
+    def __init__(self, off, col, w=None):
+        self.off, self.col, self.n, self.m = _ref_csr(off, col)
+        self.w = None if w is None else _f32(w)
+        R = ref()
+        R.ref_graph_create.restype = c_void_p
+        R.ref_graph_create.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p]
+        R.ref_graph_destroy.argtypes = [c_void_p]
+        R.ref_bfs_on.restype = c_float
+        R.ref_bfs_on.argtypes = [c_void_p, c_int, c_void_p]
+        R.ref_sssp_on.restype = c_float
+        R.ref_sssp_on.argtypes = [c_void_p, c_int, c_void_p]
+        self.handle = R.ref_graph_create(self.n, self.m, _ptr(self.off), _ptr(self.col),
+                                         None if self.w is None else _ptr(self.w))
+
+    def bfs(self, src: int):
+        d = np.empty(self.n, np.int32)
+        ms = ref().ref_bfs_on(self.handle, int(src), _ptr(d))
+        return d, float(ms)
+
+    def sssp(self, src: int):
+        d = np.empty(self.n, np.float32)
+        ms = ref().ref_sssp_on(self.handle, int(src), _ptr(d))
+        return d, float(ms)
+
+    def close(self):
+        if self.handle:
+            ref().ref_graph_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def ref_sssp(off, col, w, src: int, return_ms=False):
     off, col, n, m = _ref_csr(off, col)
     w = _f32(w)

@@ -81,6 +81,24 @@ float ref_bfs(int n, int m, const int* off, const int* col, int src, int* dist) 
   return bfs_cpu::run<ref_csr_t, vertex_t, edge_t>(csr, src, dist, pred.data());
 }
 
+// Persistent form for bench.py's reference arm: the graph is wrapped ONCE (make_csr copies 8 bytes per edge) and the
+// reference's bfs_cpu::run / sssp_cpu::run are called on it from several host threads, one source each (they only
+// read the csr_t; each call still makes the reference's own private host copy, bfs_cpu.hxx:25-27).
+void* ref_graph_create(int n, int m, const int* off, const int* col, const float* val) {
+  return new ref_csr_t(make_csr(n, m, off, col, val));
+}
+void ref_graph_destroy(void* g) { delete static_cast<ref_csr_t*>(g); }
+float ref_bfs_on(void* g, int src, int* dist) {
+  auto& csr = *static_cast<ref_csr_t*>(g);
+  std::vector<int> pred(csr.number_of_rows);
+  return bfs_cpu::run<ref_csr_t, vertex_t, edge_t>(csr, src, dist, pred.data());
+}
+float ref_sssp_on(void* g, int src, float* dist) {
+  auto& csr = *static_cast<ref_csr_t*>(g);
+  std::vector<int> pred(csr.number_of_rows);
+  return sssp_cpu::run<ref_csr_t, vertex_t, edge_t, weight_t>(csr, src, dist, pred.data());
+}
+
 float ref_sssp(int n, int m, const int* off, const int* col, const float* val, int src, float* dist) {
   auto csr = make_csr(n, m, off, col, val);
   std::vector<int> pred(n);
