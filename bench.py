@@ -247,8 +247,8 @@ def run_reference(args, rank, world):
     threads = args.cpu_threads or (os.cpu_count() or 1)
     try:
         import psutil
-        per_run = 2 * (off.nbytes + col.nbytes) + 16 * n + (1 << 28)
-        threads = max(1, min(threads, int(psutil.virtual_memory().available * 0.6 // per_run)))
+        per_run = off.nbytes + col.nbytes + 48 * n + (1 << 28)  # bfs_cpu's private CSR copy + dist + pred + queue
+        threads = max(1, min(threads, int(psutil.virtual_memory().available * 0.7 // per_run)))
     except Exception:
         threads = min(threads, 8)
     threads = max(1, min(threads, K))

@@ -79,6 +79,7 @@ _SIGNATURES = {
     "ess_filter_probe": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, POINTER(c_int64), c_void_p,
                                  c_int32]),
     "ess_uniquify_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_int64)]),
+    "ess_atomic_probe": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int]),
     "ess_frontier_to_bitmap": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]),
     "ess_bitmap_to_frontier": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_int64)]),
     "ess_bits_to_list_async": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
@@ -94,6 +95,8 @@ _SIGNATURES = {
     "ess_dist_copy_depth": (c_int, [c_void_p, c_void_p]),
     "ess_dist_exchange_kind": (c_int, [c_void_p, POINTER(c_int)]),
     "ess_dist_sssp": (c_int, [c_void_p, c_int64, POINTER(RunInfo)]),
+    "ess_dist_bfs_enactor": (c_int, [c_void_p, c_int64, c_int, c_void_p, POINTER(RunInfo)]),
+    "ess_dist_sssp_enactor": (c_int, [c_void_p, c_int64, c_int, c_void_p, POINTER(RunInfo)]),
     "ess_dist_copy_dist": (c_int, [c_void_p, c_void_p]),
     "ess_sssp_partition_relax": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "ess_sssp_partition_collect": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -383,6 +386,21 @@ def uniquify_probe(ctx: Context, g: Graph, items):
     _check(lib().ess_uniquify_probe(ctx.handle, g.handle, _p(items), int(items.numel()), _p(out), byref(cnt)),
            "ess_uniquify_probe")
     return out[: cnt.value]
+
+
+ATOMIC_OPS = {"add": 0, "min": 1, "max": 2, "exch": 3}
+
+
+def atomic_probe(ctx: Context, op: str, cell, values, serial: bool = False):
+    """math::atomic::<op>(cell, values[i]) for every i; returns the OLD values each call saw (cell is updated in
+    place). float32 or int32 tensors."""
+    import torch
+    _need_cuda(cell, values)
+    assert cell.dtype == values.dtype and cell.dtype in (torch.float32, torch.int32) and cell.numel() == 1
+    old = torch.empty_like(values)
+    _check(lib().ess_atomic_probe(ctx.handle, ATOMIC_OPS[op], int(cell.dtype == torch.float32), _p(cell), _p(values),
+                                  int(values.numel()), _p(old), int(serial)), "ess_atomic_probe")
+    return old
 
 
 def frontier_to_bitmap(ctx: Context, items, universe: int):

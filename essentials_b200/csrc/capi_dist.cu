@@ -5,6 +5,8 @@
  */
 #include "capi_dispatch.hxx"
 #include "capi_frontier.hxx"
+#include <gunrock/algorithms/bfs.hxx>
+#include <gunrock/algorithms/sssp.hxx>
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -100,10 +102,13 @@ inline int fail_pull_via_step() {
 }
 
 /// Copies (out_count, aux2) of the operator counter block into the caller's two int64 and re-zeroes the block.
-static __global__ void export_counts_kernel(b200::counter_t* counters, b200::counter_t* counts) {
+static __global__ void export_counts_kernel(b200::counter_t* counters, b200::counter_t* counts, bool has_edges) {
+  // has_edges: aux2 holds Σdeg of the vertices found (pull_step_kernel); pull_chunk_kernel does not read row bounds
+  // of the vertices it adopts, so Beamer's m_f is simply not updated on bottom-up levels (only the top-down rule
+  // uses it, and absorb_kernel supplies it there)
   if (threadIdx.x == 0) {
     counts[0] += counters[scratch_t::out_count];
-    counts[1] += counters[scratch_t::aux2];
+    if (has_edges) counts[1] += counters[scratch_t::aux2];
   }
   if (threadIdx.x < scratch_t::n_slots) counters[threadIdx.x] = 0;
 }
@@ -125,10 +130,18 @@ int partition_pull(ess_context_t ctx, graph_t& G, int64_t row_begin, int32_t lev
   };
   scratch.zero(stream);
   c->profiler().begin(gcuda::profiler_t::pull_step, stream);
-  operators::advance::kernels::pull_step_kernel<<<gcuda::persistent_grid(*c, (std::size_t(A.n) + 255) / 256, 6), 256,
-                                                  0, stream>>>(A, adopt, d_frontier_bits, d_next_slice,
-                                                               d_visited_bits + (row_begin >> 5), scratch.d);
-  export_counts_kernel<<<1, 32, 0, stream>>>(scratch.d, reinterpret_cast<b200::counter_t*>(d_counts));
+  namespace k = operators::advance::kernels;
+  const bool chunked = k::pull_engine() != 0;
+  if (chunked) {  // same kernel as the single-GPU bottom-up level: rows, visited and next words are the owned range
+    auto kernel = k::pull_chunk_kernel<int32_t, edge_t, float, decltype(adopt)>;
+    const std::size_t chunks = ((std::size_t(A.n) + 31) / 32 + k::pull_chunk_words - 1) / k::pull_chunk_words;
+    kernel<<<gcuda::full_grid(*c, kernel, (chunks + 7) / 8), 256, 0, stream>>>(
+        A, adopt, d_frontier_bits, d_next_slice, d_visited_bits + (row_begin >> 5), scratch.d);
+  } else {
+    k::pull_step_kernel<<<gcuda::persistent_grid(*c, (std::size_t(A.n) + 255) / 256, 6), 256, 0, stream>>>(
+        A, adopt, d_frontier_bits, d_next_slice, d_visited_bits + (row_begin >> 5), scratch.d);
+  }
+  export_counts_kernel<<<1, 32, 0, stream>>>(scratch.d, reinterpret_cast<b200::counter_t*>(d_counts), !chunked);
   c->profiler().end(stream, 2);
   scratch.clean = true;  // export_counts_kernel re-zeroed the block
   error::check_last("partition pull");
@@ -612,6 +625,7 @@ struct ess_dist_s {
   bool sssp_peer_tried = false, sssp_peer_ready = false;
   unsigned* done_counter = nullptr;  // device word of raise_flags_when_grid_done
   unsigned* timed_out = nullptr;     // pinned, mapped
+  std::shared_ptr<gunrock::gcuda::partition_t> partition;  // NCCL bound to the operator-API partition descriptor
   ~ess_dist_s() {
     for (int p = 0; p < world && p < max_peers; ++p)
       if (p != rank && peers.base[p]) cudaIpcCloseMemHandle(peers.base[p]);
@@ -753,8 +767,100 @@ int ess_dist_create(ess_context_t ctx, ess_graph_t g, int rank, int world, int64
     d->peer_ready = d->counts_host[0] == 1;
     if (d->timed_out) *d->timed_out = 0;
   }
+  // the operator-API form of the partitioned run (operators::exchange, enactor_t::enact): bind NCCL to the context
+  {
+    auto part = std::make_shared<gcuda::partition_t>();
+    part->rank = rank;
+    part->world = world;
+    part->n_global = n_global;
+    part->per = d->per;
+    ncclComm_t comm = d->comm;
+    part->all_gather = [comm](const void* send, void* recv, std::size_t bytes, cudaStream_t st) {
+      nccl_check(nccl().AllGather(send, recv, bytes, ncclUint8, comm, st), "partition all_gather");
+    };
+    part->all_reduce_sum = [comm](long long* values, std::size_t count, cudaStream_t st) {
+      nccl_check(nccl().AllReduce(values, values, count, ncclInt64, ncclSum, comm, st), "partition all_reduce");
+    };
+    part->all_to_all_v = [comm, rank, world](const void* send, const std::size_t* send_bytes,
+                                             const std::size_t* send_off, void* recv, const std::size_t* recv_bytes,
+                                             const std::size_t* recv_off, cudaStream_t st) {
+      const auto* s8 = static_cast<const unsigned char*>(send);
+      auto* r8 = static_cast<unsigned char*>(recv);
+      if (send_bytes[rank])  // own records never touch the network
+        cudaMemcpyAsync(r8 + recv_off[rank], s8 + send_off[rank], send_bytes[rank], cudaMemcpyDeviceToDevice, st);
+      nccl_check(nccl().GroupStart(), "group");
+      for (int p = 0; p < world; ++p) {
+        if (p == rank) continue;
+        if (send_bytes[p]) nccl_check(nccl().Send(s8 + send_off[p], send_bytes[p], ncclUint8, p, comm, st), "send");
+        if (recv_bytes[p]) nccl_check(nccl().Recv(r8 + recv_off[p], recv_bytes[p], ncclUint8, p, comm, st), "recv");
+      }
+      nccl_check(nccl().GroupEnd(), "group");
+    };
+    d->partition = part;
+  }
   *out = d.release();
   return 0;
+  ESS_CATCH
+}
+
+}  // extern "C"
+
+namespace {
+/// gunrock::bfs::run / sssp::run on the owned rows with the partitioned context: the SAME enactor loop as on one GPU
+/// (prepare_frontier -> while(!is_converged) loop()), operators::exchange routing each level's frontier to the owners.
+template <typename graph_t, typename body_t>
+int run_partitioned(ess_dist_t d, graph_t view, body_t body) {
+  view.get_properties().row_offset = d->row_begin;
+  view.get_properties().global_vertices = d->n_global;
+  auto& mc = *d->ctx->ctx;
+  mc.set_partition(d->partition);
+  try {
+    body(view);
+  } catch (...) {
+    mc.set_partition(nullptr);
+    throw;
+  }
+  mc.set_partition(nullptr);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int ess_dist_bfs_enactor(ess_dist_t d, int64_t source, int lb, int32_t* d_depth_global, ess_run_info* info) {
+  ESS_TRY
+  if (!d || !d_depth_global) return ess::fail("ess_dist_bfs_enactor: null argument");
+  if (source < 0 || source >= d->n_global) return ess::fail("ess_dist_bfs_enactor: source out of range");
+  return ess::with_load_balance(lb, [&](auto lbc) -> int {
+    constexpr auto LB = decltype(lbc)::value;
+    ESS_WITH_GRAPH(d->graph, G, {
+      return run_partitioned(d, G, [&](auto& view) {
+        int32_t src = int32_t(source);
+        int iters = 0;
+        const float ms = bfs::run<LB, operators::advance_direction_t::forward>(
+            view, src, d_depth_global, (int32_t*)nullptr, d->ctx->ctx, enactor_properties_t(), nullptr, &iters);
+        ess::fill_info(info, ms, iters);
+      });
+    })
+  });
+  ESS_CATCH
+}
+
+int ess_dist_sssp_enactor(ess_dist_t d, int64_t source, int lb, float* d_dist_global, ess_run_info* info) {
+  ESS_TRY
+  if (!d || !d_dist_global) return ess::fail("ess_dist_sssp_enactor: null argument");
+  if (source < 0 || source >= d->n_global) return ess::fail("ess_dist_sssp_enactor: source out of range");
+  return ess::with_load_balance(lb, [&](auto lbc) -> int {
+    constexpr auto LB = decltype(lbc)::value;
+    ESS_WITH_GRAPH(d->graph, G, {
+      return run_partitioned(d, G, [&](auto& view) {
+        int32_t src = int32_t(source);
+        int iters = 0;
+        const float ms = sssp::run<LB>(view, src, d_dist_global, (int32_t*)nullptr, d->ctx->ctx, &iters);
+        ess::fill_info(info, ms, iters);
+      });
+    })
+  });
   ESS_CATCH
 }
 

@@ -90,9 +90,55 @@ int filter_probe(ess_context_t ctx, graph_t& G, const int32_t* d_in, int64_t siz
   return 0;
 }
 
+/// math::atomic::{add,min,max,exch} probe: old[i] = atomic::<op>(cell, values[i]). serial != 0 runs all updates in
+/// one thread (deterministic order: old[i] is the running result before values[i]); otherwise one thread per value.
+template <int OP, typename T>
+__global__ void atomic_probe_kernel(T* cell, const T* __restrict__ values, int64_t n, T* __restrict__ old, int serial) {
+  auto apply = [&](int64_t i) {
+    T before;
+    if constexpr (OP == 0) before = math::atomic::add(cell, values[i]);
+    if constexpr (OP == 1) before = math::atomic::min(cell, values[i]);
+    if constexpr (OP == 2) before = math::atomic::max(cell, values[i]);
+    if constexpr (OP == 3) before = math::atomic::exch(cell, values[i]);
+    old[i] = before;
+  };
+  if (serial) {
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      for (int64_t i = 0; i < n; ++i) apply(i);
+  } else {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) apply(i);
+  }
+}
+
+template <typename T>
+int atomic_probe(ess_context_t ctx, int op, T* cell, const T* values, int64_t n, T* old, int serial) {
+  auto stream = ctx->single()->stream();
+  const unsigned grid = serial ? 1u : unsigned(n < 256 * 592 ? (n + 255) / 256 : 592);
+  switch (op) {
+    case 0: atomic_probe_kernel<0><<<grid ? grid : 1, 256, 0, stream>>>(cell, values, n, old, serial); break;
+    case 1: atomic_probe_kernel<1><<<grid ? grid : 1, 256, 0, stream>>>(cell, values, n, old, serial); break;
+    case 2: atomic_probe_kernel<2><<<grid ? grid : 1, 256, 0, stream>>>(cell, values, n, old, serial); break;
+    case 3: atomic_probe_kernel<3><<<grid ? grid : 1, 256, 0, stream>>>(cell, values, n, old, serial); break;
+    default: return ess::fail("ess_atomic_probe: op must be 0 add, 1 min, 2 max, 3 exch");
+  }
+  error::check_last("ess_atomic_probe");
+  ctx->single()->synchronize();
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int ess_atomic_probe(ess_context_t ctx, int op, int is_float, void* d_cell, const void* d_values, int64_t n,
+                     void* d_old, int serial) {
+  ESS_TRY
+  if (!ctx || !d_cell || (n > 0 && (!d_values || !d_old))) return ess::fail("ess_atomic_probe: null argument");
+  if (is_float) return atomic_probe<float>(ctx, op, (float*)d_cell, (const float*)d_values, n, (float*)d_old, serial);
+  return atomic_probe<int32_t>(ctx, op, (int32_t*)d_cell, (const int32_t*)d_values, n, (int32_t*)d_old, serial);
+  ESS_CATCH
+}
+
 
 int ess_advance_probe(ess_context_t ctx, ess_graph_t g, int lb, int direction, const int32_t* d_frontier,
                       int64_t frontier_size, int32_t* d_out, int64_t out_capacity, int64_t* out_count,

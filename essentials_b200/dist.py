@@ -391,6 +391,29 @@ class NativePartitionedBFS:
                 "relaxed_edges": int(info.reserved[1]), "enact_ms": float(info.enact_ms),
                 "exchange": "peer-memory" if int(info.reserved[2]) else "nccl"}
 
+    def bfs_enactor(self, source: int, lb: str = "merge_path"):
+        """gunrock::bfs::run through the enactor contract with the partitioned context (ess_dist_bfs_enactor):
+        advance::execute<lb> + operators::exchange::execute per level. Returns (owned depth slice, info)."""
+        ess = self.ess
+        if getattr(self, "_labels_i32", None) is None:
+            self._labels_i32 = torch.empty(self.n_global, dtype=torch.int32, device=self.device)
+        info = ess.RunInfo()
+        ess._check(ess.lib().ess_dist_bfs_enactor(self.handle, int(source), ess.LOAD_BALANCE[lb],
+                                                  ess._p(self._labels_i32), byref(info)), "ess_dist_bfs_enactor")
+        lo = self.row_begin
+        return self._labels_i32[lo:lo + self.per], {"iterations": int(info.iterations), "enact_ms": float(info.enact_ms)}
+
+    def sssp_enactor(self, source: int, lb: str = "merge_path"):
+        """gunrock::sssp::run through the enactor contract with the partitioned context (ess_dist_sssp_enactor)."""
+        ess = self.ess
+        if getattr(self, "_labels_f32", None) is None:
+            self._labels_f32 = torch.empty(self.n_global, dtype=torch.float32, device=self.device)
+        info = ess.RunInfo()
+        ess._check(ess.lib().ess_dist_sssp_enactor(self.handle, int(source), ess.LOAD_BALANCE[lb],
+                                                   ess._p(self._labels_f32), byref(info)), "ess_dist_sssp_enactor")
+        lo = self.row_begin
+        return self._labels_f32[lo:lo + self.per], {"iterations": int(info.iterations), "enact_ms": float(info.enact_ms)}
+
     def _fetch_dist(self):
         if getattr(self, "dist_local", None) is None:
             self.dist_local = torch.empty(self.per, dtype=torch.float32, device=self.device)

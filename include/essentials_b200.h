@@ -178,6 +178,14 @@ ESS_API int ess_filter_probe(ess_context_t ctx, ess_graph_t g, int alg, const in
 ESS_API int ess_uniquify_probe(ess_context_t ctx, ess_graph_t g, const int32_t* d_in, int64_t size, int32_t* d_out,
                                int64_t* out_count);
 
+/* math::atomic::{add,min,max,exch} (include/gunrock/util/math.hxx:77-129; float min/max:
+ * include/gunrock/cuda/atomic_functions.hxx:36-123). d_old[i] = atomic::<op>(d_cell, d_values[i]) — the wrappers
+ * return the value the cell held BEFORE the update, which user lambdas compare against (bfs.hxx:96-99,
+ * sssp.hxx:121-127). op: 0 add, 1 min, 2 max, 3 exch; is_float selects float or int32 cells; serial != 0 applies the
+ * updates in index order from one thread (deterministic), otherwise one thread per value. */
+ESS_API int ess_atomic_probe(ess_context_t ctx, int op, int is_float, void* d_cell, const void* d_values, int64_t n,
+                             void* d_old, int serial);
+
 /* frontier sparse -> dense (bitmap, 1 bit per vertex; d_words: ceil(universe/32)+1 x uint32) and back
  * (ascending within 1024-vertex groups). Stand for the conversions SURVEY.md K14 R3/R4 lists; the
  * reference's boolmap_frontier_t (frontier/experimental/boolmap_frontier.hxx:25-202) has none. */
@@ -267,6 +275,17 @@ ESS_API int ess_sssp_partition_relax(ess_context_t ctx, ess_graph_t g, const int
 ESS_API int ess_sssp_partition_collect(ess_context_t ctx, ess_graph_t g, const float* d_reduced, float* d_dist_local,
                                        int32_t* d_active_list, int64_t* d_counts);
 ESS_API int ess_dist_sssp(ess_dist_t d, int64_t source, ess_run_info* info);
+
+/* The operator-API form of the partitioned run: gunrock::bfs::run / gunrock::sssp::run
+ * (include/gunrock/algorithms/bfs.hxx:151-176, sssp.hxx:155-185) on this rank's rows with a gcuda::multi_context_t
+ * that carries the partition descriptor — the SAME enactor contract as on one GPU (prepare_frontier ->
+ * while(!is_converged) loop(), include/gunrock/framework/enactor.hxx:243-254), loop() = advance::execute<lb>
+ * followed by operators::exchange::execute, which routes each level's frontier to the owners over NCCL
+ * (the reference throws on more than one context, framework/operators/advance/advance.hxx:125-128).
+ * d_depth_global / d_dist_global: caller-owned arrays of n_global entries; on return the OWNED slice
+ * [rank*n/P, (rank+1)*n/P) holds the result (other entries are pruning bounds). Collective: every rank calls it. */
+ESS_API int ess_dist_bfs_enactor(ess_dist_t dist, int64_t source, int lb, int32_t* d_depth_global, ess_run_info* info);
+ESS_API int ess_dist_sssp_enactor(ess_dist_t dist, int64_t source, int lb, float* d_dist_global, ess_run_info* info);
 ESS_API int ess_dist_copy_dist(ess_dist_t d, float* d_out);
 
 #ifdef __cplusplus

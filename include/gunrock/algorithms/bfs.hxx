@@ -9,6 +9,9 @@
  *   bfs::run(G, src, dist, pred)                                   == reference behaviour (block_mapped push)
  *   bfs::run<load_balance_t::merge_path, advance_direction_t::optimized>(...)  = push/pull switching
  * Depths are an order-independent fixed point, so every variant returns the same array.
+ * With a partitioned context (gcuda::partition_t, one process per GPU) the same loop body runs on the owned rows and
+ * operators::exchange::execute routes each level's discoveries to their owners: `distances` is then a full-length
+ * array whose owned slice is the result.
  */
 #pragma once
 
@@ -44,7 +47,7 @@ struct problem_t : gunrock::problem_t<graph_t> {
   void init() override {}
   void reset() override {
     auto* ctx = this->get_single_context();
-    const std::size_t n = std::size_t(this->get_graph().get_number_of_vertices());
+    const std::size_t n = this->label_count();  // global length in a partitioned run
     b200::fill(*ctx, result.distances, n, std::numeric_limits<vertex_t>::max());
     b200::set_one(*ctx, result.distances + param.single_source, vertex_t(0));
   }
@@ -67,7 +70,9 @@ struct enactor_t : gunrock::enactor_t<problem_t> {
   }
 
   void prepare_frontier(frontier_t* f, gcuda::multi_context_t& context) override {
-    f->push_back(this->get_problem()->param.single_source);
+    // partitioned run: only the owner starts with the source (as a local row id)
+    const vertex_t row = this->get_problem()->local_row(this->get_problem()->param.single_source);
+    if (util::limits::is_valid(row)) f->push_back(row);
   }
 
   void loop(gcuda::multi_context_t& context) override {
@@ -95,6 +100,12 @@ struct enactor_t : gunrock::enactor_t<problem_t> {
       operators::advance::execute<lb, direction>(G, E, operators::advance::directional(search, adopt), context);
     } else {
       operators::advance::execute<lb, direction>(G, E, search, context);
+    }
+    if (context.partition && context.partition->world > 1) {
+      // 1-D partitioned run: discovered vertices go to their owners, who keep min(depth) and de-duplicate
+      error::throw_if_exception(direction == operators::advance_direction_t::optimized,
+                                "partitioned direction-optimized BFS is driven by ess_dist_bfs");
+      operators::exchange::execute(G, E, distances, context);
     }
   }
 };

@@ -62,7 +62,7 @@ struct problem_t : gunrock::problem_t<graph_t> {
   void reset() override {
     auto* ctx = this->get_single_context();
     const std::size_t n = std::size_t(this->get_graph().get_number_of_vertices());
-    b200::fill(*ctx, result.distances, n, std::numeric_limits<weight_t>::max());
+    b200::fill(*ctx, result.distances, this->label_count(), std::numeric_limits<weight_t>::max());
     b200::set_one(*ctx, result.distances + param.single_source, weight_t(0));
     b200::fill(*ctx, visited.data(), n, vertex_t(-1));
   }
@@ -90,7 +90,9 @@ struct enactor_t : gunrock::enactor_t<problem_t> {
   enactor_t(problem_t* _problem, std::shared_ptr<gcuda::multi_context_t> _context) : base_t(_problem, _context) {}
 
   void prepare_frontier(frontier_t* f, gcuda::multi_context_t& context) override {
-    f->push_back(this->get_problem()->param.single_source);
+    // partitioned run: only the owner starts with the source (as a local row id)
+    const vertex_t row = this->get_problem()->local_row(this->get_problem()->param.single_source);
+    if (util::limits::is_valid(row)) f->push_back(row);
   }
 
   void loop(gcuda::multi_context_t& context) override {
@@ -100,6 +102,21 @@ struct enactor_t : gunrock::enactor_t<problem_t> {
     auto distances = P->result.distances;
     auto visited = P->visited.data();
     const vertex_t iteration = vertex_t(this->iteration);
+    if (context.partition && context.partition->world > 1) {
+      // 1-D partitioned run: relax the owned rows against the full-length label array, then route every improved
+      // neighbour to its owner, who keeps the minimum and de-duplicates (operators::exchange); the bypass filter
+      // / fused uniquify of the single-GPU loop is subsumed by the owner-side de-duplication
+      static_assert(!near_far || true, "");
+      error::throw_if_exception(near_far, "partitioned SSSP uses the level loop, not the near-far kernel");
+      auto shortest = [distances] __host__ __device__(vertex_t const& source, vertex_t const& neighbor,
+                                                      edge_t const& edge, weight_t const& weight) -> bool {
+        const weight_t candidate = thread::load(&distances[source]) + weight;
+        return candidate < math::atomic::min(&distances[neighbor], candidate);
+      };
+      operators::advance::execute<lb>(G, E, shortest, context);
+      operators::exchange::execute(G, E, distances, context);
+      return;
+    }
 
     // near-far form of the same relaxation: inside the persistent kernel the labels are read through L2
     auto relax = [distances] __host__ __device__(vertex_t const& source, vertex_t const& neighbor,

@@ -14,6 +14,8 @@
 #pragma once
 
 #include <cstdint>
+#include <functional>
+#include <memory>
 #include <unordered_map>
 #include <vector>
 #include <cuda_runtime_api.h>
@@ -291,15 +293,42 @@ inline void standard_context_t::print_properties() {
               _props.minor, _props.multiProcessorCount, _props.totalGlobalMem / 1e9, _props.l2CacheSize / 1e6);
 }
 
+/**
+ * @brief Partition descriptor of a one-process-per-GPU run (1-D vertex partition: rank r owns the global vertices
+ * [r * per, (r + 1) * per)). The three collectives are stream-ordered operations on device buffers and are bound
+ * by the host application (essentials_b200's C ABI binds NCCL over NVLink; a single-rank binding is trivial), so
+ * this header tree has no link-time dependency on a communication library. Consumed by operators::exchange and
+ * by enactor_t::enact() / is_converged().
+ */
+struct partition_t {
+  int rank = 0, world = 1;
+  long long n_global = 0, per = 0;
+  /// recv[p * bytes .. (p+1) * bytes) = the `bytes` bytes rank p passed as `send`.
+  std::function<void(const void* send, void* recv, std::size_t bytes, cudaStream_t)> all_gather;
+  /// send + send_offset[p] .. : send_bytes[p] bytes for rank p; recv + recv_offset[p] ..: recv_bytes[p] bytes from p.
+  std::function<void(const void* send, const std::size_t* send_bytes, const std::size_t* send_offset, void* recv,
+                     const std::size_t* recv_bytes, const std::size_t* recv_offset, cudaStream_t)>
+      all_to_all_v;
+  /// In-place sum over all ranks of `count` int64 values.
+  std::function<void(long long* values, std::size_t count, cudaStream_t)> all_reduce_sum;
+};
+
 class multi_context_t {
  public:
   std::vector<standard_context_t*> contexts;
   std::vector<device_id_t> devices;
   static constexpr std::size_t MAX_NUMBER_OF_GPUS = 1024;
 
-  /// 1-D partition descriptor for one-process-per-GPU runs (rank owns a contiguous vertex range).
+  /// 1-D partition descriptor for one-process-per-GPU runs (rank owns a contiguous vertex range); null = the
+  /// context's device holds the whole graph. rank / world_size mirror it.
   int rank = 0;
   int world_size = 1;
+  std::shared_ptr<partition_t> partition;
+  void set_partition(std::shared_ptr<partition_t> p) {
+    partition = std::move(p);
+    rank = partition ? partition->rank : 0;
+    world_size = partition ? partition->world : 1;
+  }
 
   template <typename device_list_t, typename = decltype(std::declval<device_list_t>().begin())>
   explicit multi_context_t(const device_list_t& _devices) : devices(_devices.begin(), _devices.end()) {

@@ -105,6 +105,11 @@ struct enactor_t {
   direction_state_t<vertex_t, edge_t> direction;
   /// "already emitted in this call" bitmap of operators::advance::execute_unique (all clear between calls).
   typename direction_state_t<vertex_t, edge_t>::bits_t unique_seen;
+  /// 1-D partitioned runs (context->partition set): frontier size summed over all ranks, maintained by
+  /// operators::exchange::execute and by enact() after prepare_frontier(); -1 = not partitioned.
+  long long global_frontier_size = -1;
+  memory::device_array_t<unsigned long long> exchange_counts;  ///< operators::exchange scratch
+  memory::device_array_t<uint2> exchange_send, exchange_recv;
 
   enactor_t(const enactor_t&) = delete;
   enactor_t& operator=(const enactor_t&) = delete;
@@ -148,6 +153,15 @@ struct enactor_t {
   float enact() {
     auto single_context = context->get_context(0);
     prepare_frontier(get_input_frontier(), *context);
+    if (context->partition && context->partition->world > 1) {  // partitioned: convergence is a global property
+      memory::device_array_t<long long> size(1);
+      long long mine = (long long)get_input_frontier()->get_number_of_elements();
+      cudaMemcpyAsync(size.data(), &mine, sizeof(mine), cudaMemcpyHostToDevice, single_context->stream());
+      context->partition->all_reduce_sum(size.data(), 1, single_context->stream());
+      cudaMemcpyAsync(&mine, size.data(), sizeof(mine), cudaMemcpyDeviceToHost, single_context->stream());
+      single_context->synchronize();
+      global_frontier_size = mine;
+    }
     auto& timer = single_context->timer();
     timer.begin();
     while (!is_converged(*context)) {
@@ -160,7 +174,10 @@ struct enactor_t {
 
   virtual void loop(gcuda::multi_context_t& context) = 0;
   virtual void prepare_frontier(frontier_t* f, gcuda::multi_context_t& context) {}
-  virtual bool is_converged(gcuda::multi_context_t& context) { return active_frontier->is_empty(); }
+  virtual bool is_converged(gcuda::multi_context_t& context) {
+    if (global_frontier_size >= 0) return global_frontier_size == 0;  // partitioned run: empty on every rank
+    return active_frontier->is_empty();
+  }
   virtual void finalize(gcuda::multi_context_t& context) {}
 };
 

@@ -133,7 +133,13 @@ void expand(graph_t& G, operator_t op, frontier_t* input, frontier_t* output, wo
     const counter_t capacity = has_output ? counter_t(output->get_capacity()) : counter_t(0);
     counter_t* C = scratch.d;
 
-    if constexpr (lb == load_balance_t::thread_mapped || lb == load_balance_t::block_mapped) {
+    // merge_path over `input = graph` (PageRank push, SpMV): the frontier is every vertex in id order, so the
+    // scan + compaction pass of merge-path (16-24 bytes written and re-read per vertex) buys nothing over
+    // block-mapped tiles of 256 consecutive rows with dynamic tickets and hub deferral; same operator calls
+    constexpr bool as_block_mapped =
+        lb == load_balance_t::block_mapped ||
+        ((lb == load_balance_t::merge_path || lb == load_balance_t::merge_path_v2) && graph_input && quad_types);
+    if constexpr (lb == load_balance_t::thread_mapped || as_block_mapped) {
       const bool guard = has_output && (long double)(nf) * (long double)(maxdeg) > (long double)(capacity);
       if (guard) {
         prof.begin(profiler_t::work_prepare, stream);

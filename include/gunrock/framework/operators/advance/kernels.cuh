@@ -72,6 +72,7 @@ __device__ __forceinline__ bool visit_edge(const graph::adjacency_t<vertex_t, ed
     if ((visited[unsigned(neighbor) >> 5] >> (unsigned(neighbor) & 31u)) & 1u) return false;
   }
   weight_t weight = A.values ? __ldg(A.values + edge) : weight_t(1);
+  source += A.source_offset;  // 1-D partition: operators see global vertex ids
   bool keep = op(source, neighbor, edge, weight);
   if constexpr (policy == visit_t::test_and_set) {
     if (keep) {
@@ -178,7 +179,7 @@ __device__ __forceinline__ void expand_tile(const graph::adjacency_t<vertex_t, e
       for (int i = 0; i < tile_items; ++i)
         if ((live & (1u << i)) && !((old[i] >> (unsigned(nbr[i]) & 31u)) & 1u)) {
           const weight_t weight = A.values ? __ldg(A.values + eid[i]) : weight_t(1);
-          if (call_pull(op, src[i], nbr[i], eid[i], weight)) keep |= 1u << i;
+          if (call_pull(op, vertex_t(src[i] + A.source_offset), nbr[i], eid[i], weight)) keep |= 1u << i;
         }
       if constexpr (count_fresh_edges_in_kernel) {
         edge_t lo[tile_items], hi[tile_items];

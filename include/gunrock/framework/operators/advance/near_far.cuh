@@ -63,6 +63,146 @@ enum near_far_exit_t : int {
 
 constexpr unsigned near_far_inf_bits = 0x7f800000u;
 
+/**
+ * @brief One near level, shared by the grid-wide and the cluster kernel: every lane takes one vertex of the level's
+ * queue; its edges are relaxed 4 per batch so that the column/weight loads, the operators (atomics) and the routing
+ * (priority loads, stamp / flag exchanges) of a batch are in flight together — the edge-at-a-time loop this
+ * replaces paid one full dependent chain of L2 round trips PER EDGE, most of a level's 13-15 us on the grid. A
+ * neighbour the operator improved joins the next near queue (priority < threshold, once per level: stamp) or the
+ * far pile (once: flag); the warp claims its slots with ONE atomic per queue and batch. `out_count` / `far_count`
+ * may live in global or in distributed shared memory. Called by all threads of the kernel.
+ */
+template <typename vertex_t, typename edge_t, typename weight_t, typename operator_t, typename priority_t>
+__device__ __forceinline__ void near_far_expand_level(
+    const graph::adjacency_t<vertex_t, edge_t, weight_t>& A, operator_t& op, priority_t& priority,
+    const vertex_t* __restrict__ q_in, unsigned long long n_in, vertex_t* __restrict__ q_out,
+    unsigned long long* out_count, vertex_t* __restrict__ far_out, unsigned long long* far_count, float threshold,
+    int next_level, int* queue_stamp, int* far_flag, unsigned long long capacity, unsigned long long tid,
+    unsigned long long threads, unsigned long long& my_relax, bool& overflowed) {
+  const unsigned lane = b200::lane_id();
+  // Routes up to 4 improved neighbours per lane: priorities, stamps and flags of the batch are in flight
+  // together, and the whole warp claims its queue slots with ONE distributed-shared-memory atomic per queue.
+  auto route4 = [&](const bool (&improved)[4], const vertex_t (&u)[4]) {  // called by all 32 lanes
+    float pri[4];
+    bool to_near[4], to_far[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pri[j] = improved[j] ? float(priority(u[j])) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      to_near[j] = to_far[j] = false;
+      if (improved[j]) {
+        if (pri[j] < threshold)
+          to_near[j] = atomicExch(queue_stamp + u[j], next_level) != next_level;
+        else
+          to_far[j] = atomicExch(far_flag + u[j], 1) == 0;
+      }
+    }
+    unsigned near_votes[4], far_votes[4], n_near = 0, n_far_new = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      near_votes[j] = __ballot_sync(b200::full_mask, to_near[j]);
+      far_votes[j] = __ballot_sync(b200::full_mask, to_far[j]);
+      n_near += __popc(near_votes[j]);
+      n_far_new += __popc(far_votes[j]);
+    }
+    if ((n_near | n_far_new) == 0) return;  // warp-uniform
+    unsigned long long base_near = 0, base_far = 0;
+    if (lane == 0) {
+      if (n_near) base_near = atomicAdd(out_count, (unsigned long long)n_near);
+      if (n_far_new) base_far = atomicAdd(far_count, (unsigned long long)n_far_new);
+    }
+    base_near = __shfl_sync(b200::full_mask, base_near, 0);
+    base_far = __shfl_sync(b200::full_mask, base_far, 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (to_near[j]) {
+        const unsigned long long at = base_near + __popc(near_votes[j] & b200::lanes_below(lane));
+        if (at < capacity) q_out[at] = u[j]; else overflowed = true;
+      }
+      if (to_far[j]) {
+        const unsigned long long at = base_far + __popc(far_votes[j] & b200::lanes_below(lane));
+        if (at < capacity) far_out[at] = u[j]; else overflowed = true;
+      }
+      base_near += __popc(near_votes[j]);
+      base_far += __popc(far_votes[j]);
+    }
+  };
+
+  for (unsigned long long base = (tid >> 5) << 5; base < n_in; base += threads) {
+    const unsigned long long i = base + lane;
+    vertex_t v = 0;
+    edge_t beg = 0, deg = 0;
+    if (i < n_in) {
+      v = q_in[i];
+      beg = A.offsets[v];
+      deg = A.offsets[v + 1] - beg;
+    }
+    unsigned long_lanes = __ballot_sync(b200::full_mask, deg >= 32);
+    while (long_lanes) {  // adjacency lists of >= 32 edges: the whole warp, coalesced, 4 strides per batch
+      const int owner = __ffs(long_lanes) - 1;
+      long_lanes &= long_lanes - 1;
+      const vertex_t src = __shfl_sync(b200::full_mask, v, owner);
+      const edge_t b = __shfl_sync(b200::full_mask, beg, owner);
+      const edge_t e_end = b + __shfl_sync(b200::full_mask, deg, owner);
+      for (edge_t e0 = b; e0 < e_end; e0 += 128) {
+        bool improved[4];
+        vertex_t u[4];
+        edge_t edge[4];
+        weight_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          edge[j] = e0 + edge_t(32 * j) + edge_t(lane);
+          u[j] = 0, w[j] = weight_t(1);
+          if (edge[j] < e_end) {
+            u[j] = __ldg(A.indices + edge[j]);
+            if (A.values) w[j] = __ldg(A.values + edge[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          improved[j] = false;
+          if (edge[j] < e_end) {
+            vertex_t s = src;
+            ++my_relax;
+            improved[j] = op(s, u[j], edge[j], w[j]);
+          }
+        }
+        route4(improved, u);
+      }
+    }
+    // short lists: every lane walks its own, 4 edges per batch (loads, operators and routing of a batch overlap:
+    // the serial edge-at-a-time loop cost one full dependent chain of L2 round trips PER EDGE, which at degree 4
+    // was most of a level's 13-15 us on the grid)
+    const edge_t short_deg = deg < 32 ? deg : edge_t(0);
+    const edge_t trips = b200::warp_max(short_deg);  // warp-uniform trip count keeps the ballots converged
+    for (edge_t k0 = 0; k0 < trips; k0 += 4) {
+      bool improved[4];
+      vertex_t u[4];
+      edge_t edge[4];
+      weight_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        edge[j] = beg + k0 + edge_t(j);
+        u[j] = 0, w[j] = weight_t(1);
+        if (k0 + edge_t(j) < short_deg) {
+          u[j] = __ldg(A.indices + edge[j]);
+          if (A.values) w[j] = __ldg(A.values + edge[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        improved[j] = false;
+        if (k0 + edge_t(j) < short_deg) {
+          vertex_t s = v;
+          ++my_relax;
+          improved[j] = op(s, u[j], edge[j], w[j]);
+        }
+      }
+      route4(improved, u);
+    }
+  }
+}
+
 template <typename vertex_t, typename edge_t, typename weight_t, typename operator_t, typename priority_t>
 __global__ void __launch_bounds__(256, 2)
     near_far_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op, priority_t priority,
@@ -108,54 +248,10 @@ __global__ void __launch_bounds__(256, 2)
       const int next_level = level + 1;
       if (tid == 0) st->near_count[(level + 2) % 3] = 0;  // consumed a level ago; the next level appends to it
 
-      // a neighbour that just improved goes to the next level's queue or to the far pile, once each
-      auto route = [&](vertex_t u) {
-        if (float(priority(u)) < threshold) {
-          if (atomicExch(queue_stamp + u, next_level) != next_level) {
-            const unsigned long long at = atomicAdd(out_count, 1ull);
-            if (at < capacity) q_out[at] = u; else state->overflow = 1;
-          }
-        } else if (atomicExch(far_flag + u, 1) == 0) {
-          const unsigned long long at = atomicAdd(far_count, 1ull);
-          if (at < capacity) far_out[at] = u; else state->overflow = 1;
-        }
-      };
-
-      for (unsigned long long base = (tid >> 5) << 5; base < n_in; base += threads) {
-        const unsigned long long i = base + lane;
-        vertex_t v = 0;
-        edge_t beg = 0, deg = 0;
-        if (i < n_in) {
-          v = q_in[i];
-          beg = A.offsets[v];
-          deg = A.offsets[v + 1] - beg;
-        }
-        // adjacency lists of >= 32 edges are walked by the whole warp (coalesced), short ones by their own lane
-        unsigned long_lanes = __ballot_sync(b200::full_mask, deg >= 32);
-        while (long_lanes) {
-          const int owner = __ffs(long_lanes) - 1;
-          long_lanes &= long_lanes - 1;
-          const vertex_t src = __shfl_sync(b200::full_mask, v, owner);
-          const edge_t b = __shfl_sync(b200::full_mask, beg, owner);
-          const edge_t e_end = b + __shfl_sync(b200::full_mask, deg, owner);
-          for (edge_t e = b + edge_t(lane); e < e_end; e += 32) {
-            vertex_t s = src, u = __ldg(A.indices + e);
-            edge_t edge = e;
-            weight_t w = A.values ? __ldg(A.values + e) : weight_t(1);
-            ++my_relax;
-            if (op(s, u, edge, w)) route(u);
-          }
-        }
-        if (deg < 32) {
-          for (edge_t e = beg; e < beg + deg; ++e) {
-            vertex_t s = v, u = __ldg(A.indices + e);
-            edge_t edge = e;
-            weight_t w = A.values ? __ldg(A.values + e) : weight_t(1);
-            ++my_relax;
-            if (op(s, u, edge, w)) route(u);
-          }
-        }
-      }
+      bool overflowed = false;
+      near_far_expand_level(A, op, priority, q_in, n_in, q_out, out_count, far_out, far_count, threshold, next_level,
+                            queue_stamp, far_flag, capacity, tid, threads, my_relax, overflowed);
+      if (overflowed) state->overflow = 1;
       grid.sync();
       ++level;
     }
@@ -310,72 +406,15 @@ __global__ void __launch_bounds__(1024, 1)
       const int next_level = level + 1;
       if (leader) s_ctl.near_count[(level + 2) % 3] = 0;  // read a level ago, appended to a level from now
 
-      auto route = [&](bool improved, vertex_t u) {  // called by all 32 lanes
-        bool to_near = false, to_far = false;
-        if (improved) {
-          if (float(priority(u)) < threshold)
-            to_near = atomicExch(queue_stamp + u, next_level) != next_level;
-          else
-            to_far = atomicExch(far_flag + u, 1) == 0;
-        }
-        append(to_near, u, q_out, out_count);
-        append(to_far, u, far_out, far_count);
-      };
-
-      for (unsigned long long base = (tid >> 5) << 5; base < n_in; base += threads) {
-        const unsigned long long i = base + lane;
-        vertex_t v = 0;
-        edge_t beg = 0, deg = 0;
-        if (i < n_in) {
-          v = q_in[i];
-          beg = A.offsets[v];
-          deg = A.offsets[v + 1] - beg;
-        }
-        unsigned long_lanes = __ballot_sync(b200::full_mask, deg >= 32);
-        while (long_lanes) {  // adjacency lists of >= 32 edges: the whole warp, coalesced
-          const int owner = __ffs(long_lanes) - 1;
-          long_lanes &= long_lanes - 1;
-          const vertex_t src = __shfl_sync(b200::full_mask, v, owner);
-          const edge_t b = __shfl_sync(b200::full_mask, beg, owner);
-          const edge_t e_end = b + __shfl_sync(b200::full_mask, deg, owner);
-          for (edge_t e0 = b; e0 < e_end; e0 += 32) {
-            const edge_t e = e0 + edge_t(lane);
-            bool improved = false;
-            vertex_t u = 0;
-            if (e < e_end) {
-              vertex_t s = src;
-              u = __ldg(A.indices + e);
-              edge_t edge = e;
-              weight_t w = A.values ? __ldg(A.values + e) : weight_t(1);
-              ++my_relax;
-              improved = op(s, u, edge, w);
-            }
-            route(improved, u);
-          }
-        }
-        const edge_t short_deg = deg < 32 ? deg : edge_t(0);
-        const edge_t trips = b200::warp_max(short_deg);  // warp-uniform trip count keeps the ballots converged
-        for (edge_t k = 0; k < trips; ++k) {
-          bool improved = false;
-          vertex_t u = 0;
-          if (k < short_deg) {
-            vertex_t s = v;
-            edge_t edge = beg + k;
-            u = __ldg(A.indices + edge);
-            weight_t w = A.values ? __ldg(A.values + edge) : weight_t(1);
-            ++my_relax;
-            improved = op(s, u, edge, w);
-          }
-          route(improved, u);
-        }
-      }
+      near_far_expand_level(A, op, priority, q_in, n_in, q_out, out_count, far_out, far_count, threshold, next_level,
+                            queue_stamp, far_flag, capacity, tid, threads, my_relax, overflowed);
       cluster.sync();
       ++level;
       continue;
     }
     // ------------------------------ far pile: raise the threshold, split ------------------------------
     if (n_far == 0) break;
-    if (n_far > 4 * grow_limit) {
+    if (n_far > 64 * grow_limit) {
       reason = near_far_grew;
       break;
     }

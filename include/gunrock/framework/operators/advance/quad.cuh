@@ -163,7 +163,8 @@ __device__ __forceinline__ unsigned visit_items(const graph::adjacency_t<vertex_
 #pragma unroll
       for (int i = 0; i < N; ++i)
         if (claimed & (1u << i)) {
-          if (call_pull(op, src[i >> 2], nbr[i], edge_t(e0[i >> 2] + (i & 3)), wt[i])) keep |= 1u << i;
+          if (call_pull(op, vertex_t(src[i >> 2] + A.source_offset), nbr[i], edge_t(e0[i >> 2] + (i & 3)), wt[i]))
+            keep |= 1u << i;
           if constexpr (count_fresh_edges_in_kernel)
             fresh_edges += counter_t(A.offsets[nbr[i] + 1] - A.offsets[nbr[i]]);
         }
@@ -182,7 +183,7 @@ __device__ __forceinline__ unsigned visit_items(const graph::adjacency_t<vertex_
 #pragma unroll
     for (int i = 0; i < N; ++i)
       if (live & (1u << i)) {
-        vertex_t s = src[i >> 2], d = nbr[i];
+        vertex_t s = src[i >> 2] + A.source_offset, d = nbr[i];  // 1-D partition: global source id
         edge_t e = edge_t(e0[i >> 2] + (i & 3));
         weight_t w = wt[i];
         bool k = op(s, d, e, w);  // lvalues, exactly once per live edge

@@ -15,6 +15,8 @@
 // frontier -> frontier
 #include <gunrock/framework/operators/filter/filter.hxx>
 #include <gunrock/framework/operators/uniquify/uniquify.hxx>
+// 1-D partitioned runs: frontier -> owners
+#include <gunrock/framework/operators/exchange/exchange.hxx>
 // maps and host-side composition
 #include <gunrock/framework/operators/for/for.hxx>
 #include <gunrock/framework/operators/batch/batch.hxx>

@@ -11,6 +11,7 @@
 #include <memory>
 #include <gunrock/cuda/cuda.hxx>
 #include <gunrock/graph/graph.hxx>
+#include <gunrock/util/type_limits.hxx>
 
 namespace gunrock {
 
@@ -35,6 +36,20 @@ struct problem_t {
   virtual void reset() = 0;
 
   auto get_graph() { return graph_slice; }
+  /// Length of per-vertex label arrays: the whole graph's vertex count, also when this rank holds a row range only
+  /// (1-D partitioned runs index labels by global id, see graph_properties_t::row_offset).
+  std::size_t label_count() const {
+    const auto& props = graph_slice.get_properties();
+    return props.global_vertices ? std::size_t(props.global_vertices) : std::size_t(graph_slice.get_number_of_vertices());
+  }
+  /// Local row id of a global vertex on this rank, or invalid when another rank owns it (identity when not partitioned).
+  vertex_t local_row(vertex_t v) const {
+    const auto& props = graph_slice.get_properties();
+    if (!props.global_vertices) return v;
+    const long long local = (long long)v - props.row_offset;
+    return local >= 0 && local < (long long)graph_slice.get_number_of_vertices()
+               ? vertex_t(local) : gunrock::numeric_limits<vertex_t>::invalid();
+  }
   auto get_multi_context() { return context; }
   auto get_single_context(gcuda::device_id_t device = 0) { return context->get_context(device); }
   /// Stream every kernel of this problem's algorithm is enqueued on.

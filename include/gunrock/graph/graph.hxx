@@ -34,6 +34,11 @@ struct graph_properties_t {
   bool directed{false};
   bool weighted{true};
   bool symmetric{false};  ///< B200 addition: CSC view aliases the CSR arrays (undirected graph).
+  /// B200 addition, 1-D partitioned runs: the graph holds the rows of the global vertices
+  /// [row_offset, row_offset + number_of_vertices); column ids stay global. Frontiers hold LOCAL row ids,
+  /// operators are called with the GLOBAL source id (local + row_offset), so label arrays are indexed globally.
+  long long row_offset{0};
+  long long global_vertices{0};  ///< vertices of the whole graph (0 = this graph is the whole graph)
   graph_properties_t() = default;
 };
 
@@ -415,6 +420,9 @@ struct adjacency_t {
   const vertex_t* head = nullptr;
   const edge_t* head_edge = nullptr;
   const unsigned* isolated = nullptr;  ///< bitmap of vertices without in-edges (padding bits set), or null
+  /// 1-D partition: global id of local row 0 (graph_properties_t::row_offset). Push kernels hand the operator
+  /// `local row + source_offset` as the source vertex.
+  vertex_t source_offset = 0;
 };
 
 /// The arrays an advance walks: CSR (rows -> out-neighbours) for forward, CSC (columns -> in-neighbours)
@@ -437,8 +445,10 @@ auto adjacency_of(const graph_type& G) {
     static_assert(graph_type::template contains_representation<csr_v>(),
                   "forward advance needs a graph built with view_t::csr");
     const csr_v& c = G;
-    return adjacency_t<V, E, W>{c.get_row_offsets(), c.get_column_indices(), c.get_nonzero_values(),
-                                c.get_number_of_vertices(), c.get_number_of_edges()};
+    adjacency_t<V, E, W> a{c.get_row_offsets(), c.get_column_indices(), c.get_nonzero_values(),
+                           c.get_number_of_vertices(), c.get_number_of_edges()};
+    a.source_offset = V(G.get_properties().row_offset);
+    return a;
   }
 }
 

@@ -409,6 +409,13 @@ def ref_on_ours_extra(alg: str, csr, *tensors_and_params):
         R.refours_mst.restype = c_float
         R.refours_mst.argtypes = _G + [c_void_p]
         ms = R.refours_mst(n, m, off, col, val, c_void_p(out.data_ptr()))
+    elif alg == "tc":
+        counts = torch.zeros(n, dtype=torch.int32, device=dev)
+        total = ctypes.c_ulonglong(0)
+        R.refours_tc.restype = c_float
+        R.refours_tc.argtypes = _G + [c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]
+        ms = R.refours_tc(n, m, off, col, val, c_void_p(counts.data_ptr()), ctypes.byref(total))
+        out = (counts, int(total.value))
     else:
         raise ValueError(alg)
     torch.cuda.synchronize()

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY — API-compatibility proof for the drop-in header tree.
 //
 // The REFERENCE's own, UNMODIFIED algorithm headers (include/gunrock/algorithms/{bfs,sssp,pr,ppr,kcore,color,bc,spmv,
-// hits,mst,geo,spgemm}.hxx,
+// hits,mst,geo,spgemm,tc}.hxx,
 // included by absolute path from /root/reference) are compiled against THIS repository's include/gunrock tree:
 // every `#include <gunrock/...>` inside them resolves to our headers, so their enactors run on our operators,
 // frontier, graph views, context and atomics. Built by `make -C oracle refonours` into
@@ -25,6 +25,16 @@
 #include REF_ALG(mst.hxx)   // edge frontier, filter<remove> explicit form, parallel_for element/vertex (mst.hxx:226-248)
 #include REF_ALG(geo.hxx)     // instantiated only (parallel_for + advance clients; no checker for its heuristic output)
 #include REF_ALG(spgemm.hxx)  // instantiated only (advance<block_mapped, graph -> none>, parallel_for::vertex)
+// tc.hxx hands a `[] __device__` lambda to thrust::transform_reduce (tc.hxx:113-119). CCCL 2.8 asks for that lambda's
+// return type on the HOST, where a __device__-only lambda has none, so the reference header does not compile with this
+// toolkit on its own either. The header is taken as it is; only the spelling of `__device__` is widened to
+// `__host__ __device__` while ITS text is parsed, which turns that lambda into an ordinary extended lambda. Everything
+// tc.hxx includes is already included above (#pragma once), so no other header sees the widened macro.
+#pragma push_macro("__device__")
+#undef __device__
+#define __device__ __location__(host) __location__(device)
+#include REF_ALG(tc.hxx)  // advance<block_mapped, forward, graph -> none> + graph_t::get_intersection_count (tc.hxx:99-103)
+#pragma pop_macro("__device__")
 
 using namespace gunrock;
 using namespace memory;
@@ -77,6 +87,12 @@ float refours_hits(int n, int m, int* d_off, int* d_col, float* d_val, int max_i
 }
 float refours_mst(int n, int m, int* d_off, int* d_col, float* d_val, float* d_weight) {
   REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); return gunrock::mst::run(G, d_weight);)
+}
+// Triangle counting as the reference's unit test calls it (unittests/algorithms/tc.cuh:40-41): per-vertex counts and
+// the reduced total.
+float refours_tc(int n, int m, int* d_off, int* d_col, float* d_val, int* d_counts, unsigned long long* total) {
+  REF_GUARD(auto G = make_graph(n, m, d_off, d_col, d_val); std::size_t all = 0;
+            float ms = gunrock::tc::run(G, true, d_counts, &all); if (total) *total = all; return ms;)
 }
 // Instantiation-only proofs: these two link against our operators but have no independent checker here (geo is a
 // heuristic, spgemm leaves an upper-bound layout in C), so the tests do not call them.

@@ -24,6 +24,9 @@ ap.add_argument("--nccl-exchange", action="store_true", help="ess_dist_bfs: NCCL
 ap.add_argument("--compare-exchange", action="store_true", help="time the BFS sources with both exchanges")
 ap.add_argument("--alg", default="bfs", help="bfs, sssp or bfs,sssp (one graph build for both)")
 ap.add_argument("--no-check", action="store_true", help="timing only (scales whose full graph does not fit one GPU)")
+ap.add_argument("--enactor", action="store_true",
+                help="also run gunrock::bfs::run / sssp::run through the enactor contract with the partitioned context "
+                     "(advance::execute + operators::exchange::execute per level) and compare with the single GPU")
 args = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -107,6 +110,36 @@ def check_bfs():
               "; ".join(f"{k}: n={len(v)} avg={sum(v)/len(v):.0f} max={max(v):.0f}" for k, v in agg.items()), flush=True)
 
 
+def check_enactor():
+    """The operator-API form: same enactor loop as on one GPU, frontier exchange by operators::exchange."""
+    global ok
+    for alg in algs:
+        for lb in ("merge_path", "block_mapped", "thread_mapped"):
+            for s in [0] + srcs[:2]:
+                dist.barrier()
+                if alg == "bfs":
+                    mine, info = runner.bfs_enactor(s, lb=lb)
+                    full = torch.empty(runner.n_global, dtype=torch.int32, device=dev)
+                else:
+                    mine, info = runner.sssp_enactor(s, lb=lb)
+                    full = torch.empty(runner.n_global, dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(full, mine.contiguous())
+                line = f"enactor {alg} lb={lb} src={s} iterations={info['iterations']} device={info['enact_ms']:.2f} ms"
+                if rank == 0 and not args.no_check:
+                    if alg == "bfs":
+                        want, _ = ess.bfs(ctx, g, s, lb=lb, direction="forward")
+                    else:
+                        want, _ = ess.sssp(ctx, g, s, lb=lb)
+                    same = bool(torch.equal(want, full))
+                    ok &= same
+                    line += f" equal={same}"
+                if rank == 0:
+                    print(line, flush=True)
+
+
+if args.enactor:
+    check_enactor()
+    algs = []  # the enactor form is checked on its own
 if "bfs" in algs:
     check_bfs()
     if args.compare_exchange:

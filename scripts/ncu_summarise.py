@@ -18,10 +18,10 @@ import json
 import re
 
 CLASSES = [  # first match wins
-    ("pull_step", r"pull_step_kernel"),
-    ("push_expand", r"merge_path_kernel|merge_path_small_kernel|thread_mapped|block_mapped|bucket|big_list|"
-                    r"expand_.*kernel"),
-    ("work_prepare", r"prepare_work_kernel|max_degree_kernel|degree_sum|bin_"),
+    ("pull_step", r"pull_step_kernel|pull_chunk_kernel"),
+    ("push_expand", r"merge_path_kernel|merge_path_small_kernel|merge_path_quad_kernel|merge_path_small_quad_kernel|"
+                    r"thread_mapped|block_mapped|warp_mapped|bucket|big_list|expand_.*kernel"),
+    ("work_prepare", r"prepare_work_kernel|prepare_quads_kernel|max_degree_kernel|degree_sum|bin_"),
     ("dense_state", r"init_visited_kernel|gather_bits_kernel|scatter_bits_kernel|mark_frontier_kernel|fill_kernel"),
     ("counters", r"publish_counters_kernel"),
     ("setup", r"pull_hints_kernel|isolated_bitmap_kernel|transpose"),

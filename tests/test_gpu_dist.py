@@ -40,3 +40,21 @@ def test_partitioned_sssp_two_gpus(loop):
     assert out.returncode == 0 and "DIST_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
     if loop.startswith("native"):
         assert ("exchange=nccl" if loop == "native-nccl" else "exchange=peer-memory") in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("ranks", [1, 2])
+def test_partitioned_enactor_contract(ranks):
+    """gunrock::bfs::run and gunrock::sssp::run with a partitioned gcuda::multi_context_t: the unchanged enactor loop
+    (prepare_frontier -> while(!is_converged) loop()), advance::execute<lb> on the owned rows and
+    operators::exchange::execute routing each level's frontier to the owners, must give the single-GPU depths and
+    distances bit for bit for three balancers. One rank exercises the whole path (binning, records, absorb, global
+    convergence) on a single-GPU box; two ranks add the NCCL all-to-all."""
+    if torch.cuda.device_count() < ranks:
+        pytest.skip("needs %d GPUs" % ranks)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks), "--master-addr",
+           "127.0.0.1", "--master-port", str(29530 + ranks), os.path.join(ROOT, "scripts", "dist_check.py"), "--scale",
+           "15", "--alg", "bfs,sssp", "--enactor", "--sources", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DIST_CHECK_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("enactor bfs") == 9 and out.stdout.count("enactor sssp") == 9
+    assert "equal=False" not in out.stdout

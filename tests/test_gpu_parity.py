@@ -165,6 +165,85 @@ def test_sssp_near_far_larger_graphs(ctx):
         assert info["relaxations"] >= grid.m * 0 + 1
 
 
+@pytest.mark.parametrize("cluster", [0, 1])
+def test_sssp_near_far_cluster_and_grid_kernels_agree(ctx, cluster):
+    """execute_near_far runs small levels in one thread-block cluster (DSMEM counters, hardware cluster barrier) and
+    hands over to the grid-wide cooperative kernel when a level outgrows the cluster, and back: same distances from
+    either kernel alone (knob 0) and from the mixed run (a Kronecker graph crosses the hand-over limits both ways)."""
+    ess.tune("near_far_cluster", cluster)
+    try:
+        grid = gg.grid_csr(211, 97, device="cuda")
+        off, col, val = grid.host()
+        dist, info = ess.sssp_near_far(ctx, ess.Graph(grid), 5)
+        assert np.array_equal(dist.cpu().numpy(), oracle.sssp(off, col, val, 5))
+        assert info["levels"] > 200
+        csr = gg.rmat_csr(17, weights="hash", device="cuda")  # levels far beyond 64 K vertices: grid-wide kernel
+        off, col, val = csr.host()
+        s = gg.pick_sources(csr, 1)[0]
+        dist, info = ess.sssp_near_far(ctx, ess.Graph(csr), s)
+        assert np.array_equal(dist.cpu().numpy(), oracle.sssp(off, col, val, s))
+    finally:
+        ess.tune("near_far_cluster", 1)
+
+
+def test_sssp_thresholds_make_progress_on_extreme_weight_ranges(ctx):
+    """Weights {1e-3, 1e6}: distances reach ~1e7 while delta stays ~1e-3, so (floor(d / delta) + 1) * delta and
+    threshold + delta both round to <= d in float; the near-far kernel and run_delta must still advance (they step
+    to nextafter(d)) instead of spinning, and the distances stay bit-exact."""
+    import dataclasses
+    grid = gg.grid_csr(40, 30, device="cuda")
+    rows = torch.repeat_interleave(torch.arange(grid.n, device="cuda"), grid.degrees().long())
+    lo, hi = torch.minimum(rows, grid.indices.long()), torch.maximum(rows, grid.indices.long())
+    w = torch.where(((lo * 31 + hi) % 5) == 0, 1e6, 1e-3).to(torch.float32)  # symmetric: both directions agree
+    g2 = dataclasses.replace(grid, values=w)
+    off, col, val = g2.host()
+    want = oracle.sssp(off, col, val, 0)
+    g = ess.Graph(g2)
+    d_nf, _ = ess.sssp_near_far(ctx, g, 0, delta=1e-3)
+    assert np.array_equal(d_nf.cpu().numpy(), want)
+    d_dl, _ = ess.sssp_delta(ctx, g, 0, delta=1e-3)
+    assert np.array_equal(d_dl.cpu().numpy(), want)
+
+
+def test_atomic_wrappers_return_the_old_value(ctx):
+    """math::atomic::{add,min,max,exch} hand back what the cell held BEFORE the update (user lambdas compare against
+    it: bfs `iteration + 1 < old`, sssp `candidate < old`); float min/max are single ordered-integer atomics here
+    (CAS loops in the reference), so negative values, zeros of both signs and infinities are checked explicitly."""
+    vals = torch.tensor([5.5, -2.25, 7.0, -2.25, float("inf"), -0.0, 0.0, -1e30, 3.0, float("-inf"), 1.0],
+                        dtype=torch.float32, device="cuda")
+    for op, fold in (("min", np.minimum), ("max", np.maximum), ("add", np.add), ("exch", lambda a, b: b)):
+        cell = torch.tensor([4.0], dtype=torch.float32, device="cuda")
+        v = vals if op != "add" else torch.tensor([0.5, -2.25, 7.0, 1.0, 3.0], dtype=torch.float32, device="cuda")
+        old = ess.atomic_probe(ctx, op, cell, v, serial=True).cpu().numpy()
+        run = np.float32(4.0)
+        for i, x in enumerate(v.cpu().numpy()):
+            assert old[i] == run and np.signbit(old[i]) == np.signbit(run), (op, i, old[i], run)
+            run = np.float32(fold(run, x))
+        assert cell.item() == run
+    ints = torch.tensor([9, -3, 12, -3, 2**31 - 1, -2**31, 0], dtype=torch.int32, device="cuda")
+    for op, fold in (("min", min), ("max", max), ("exch", lambda a, b: b)):
+        cell = torch.tensor([4], dtype=torch.int32, device="cuda")
+        old = ess.atomic_probe(ctx, op, cell, ints, serial=True).cpu().numpy()
+        run = 4
+        for i, x in enumerate(ints.cpu().tolist()):
+            assert int(old[i]) == run, (op, i)
+            run = fold(run, x)
+        assert cell.item() == run
+    # concurrent: the returned values are exactly the successive contents of the cell
+    big = (torch.rand(1 << 16, device="cuda") * 2000 - 1000).to(torch.float32)
+    cell = torch.tensor([2000.0], dtype=torch.float32, device="cuda")
+    old = ess.atomic_probe(ctx, "min", cell, big).cpu().numpy()
+    assert cell.item() == big.min().item()
+    improved = old > big.cpu().numpy()  # calls that lowered the cell: their `old` values are all distinct cell states
+    states = np.sort(old[improved])[::-1]
+    assert states[0] == 2000.0 and np.all(np.diff(states) < 0)
+    assert np.all(old >= cell.item())
+    total = torch.tensor([0], dtype=torch.int32, device="cuda")
+    ones = torch.ones(1 << 16, dtype=torch.int32, device="cuda")
+    old = ess.atomic_probe(ctx, "add", total, ones).cpu().numpy()
+    assert total.item() == 1 << 16 and np.array_equal(np.sort(old), np.arange(1 << 16))
+
+
 @pytest.mark.parametrize("fused", [0, 1])
 @pytest.mark.parametrize("lb", LBS)
 def test_sssp_fused_unique_level_loop(ctx, graphs, golden, lb, fused):

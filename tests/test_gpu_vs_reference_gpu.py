@@ -137,8 +137,8 @@ def test_reference_bc_and_spmv_headers_on_our_operators(ctx):
     want[s] = 0.0
     g = got.cpu().numpy().astype(np.float64)
     g[s] = 0.0
-    assert np.allclose(g, want if np.allclose(g, want, rtol=1e-4, atol=1e-4) else want / 2, rtol=1e-4, atol=1e-4), \
-        "bc dependency scores (the reference halves them for undirected graphs)"
+    # the reference accumulates 0.5 * delta per back-propagated edge ("scaled output", bc.hxx:168)
+    assert np.allclose(g, want / 2, rtol=1e-4, atol=1e-4), "bc dependency scores (Brandes / 2)"
     weighted = gg.rmat_csr(10, weights="hash", device="cuda")
     x = torch.rand(weighted.n, device="cuda")
     y, _ = oracle.ref_on_ours_extra("spmv", weighted, x)
@@ -146,6 +146,30 @@ def test_reference_bc_and_spmv_headers_on_our_operators(ctx):
     want = torch.zeros(weighted.n, device="cuda", dtype=torch.float64).index_add_(
         0, rows, (weighted.values.double() * x[weighted.indices.long()].double()))
     assert torch.allclose(y.double(), want, rtol=1e-5, atol=1e-5)
+
+
+@needs_compat
+def test_reference_tc_header_on_our_operators_golden_counts(ctx):
+    """§8f row 4: the reference's tc.hxx (advance<block_mapped, forward, graph -> none> + graph_t::get_intersection_count,
+    tc.hxx:99-103) on our operators must reproduce the reference's own golden counts
+    (unittests/algorithms/tc.cuh:24-54 and :57-93, the only hard known answers in the reference's test tree), and
+    agree with a dense-matrix triangle count on a Kronecker graph."""
+    import dataclasses
+    cases = [([0, 3, 5, 8, 10], [1, 2, 3, 0, 2, 0, 1, 3, 0, 2], [2, 1, 2, 1], 6),
+             ([0, 4, 7, 10, 12], [0, 1, 2, 3, 0, 1, 2, 0, 1, 3, 0, 2], [2, 1, 2, 1], 6)]  # second: self loops ignored
+    for off, col, per_vertex, total in cases:
+        csr = gg.CSR(len(off) - 1, len(col), torch.tensor(off, dtype=torch.int32, device="cuda"),
+                     torch.tensor(col, dtype=torch.int32, device="cuda"),
+                     torch.zeros(len(col), dtype=torch.float32, device="cuda"), "tc-golden", True)
+        (counts, all_triangles), _ = oracle.ref_on_ours_extra("tc", csr)
+        assert counts.cpu().tolist() == per_vertex and all_triangles == total
+    kron = gg.rmat_csr(9, weights="ones", device="cuda")
+    (counts, all_triangles), _ = oracle.ref_on_ours_extra("tc", kron)
+    a = torch.zeros(kron.n, kron.n, dtype=torch.float64, device="cuda")
+    rows = torch.repeat_interleave(torch.arange(kron.n, device="cuda"), kron.degrees().long())
+    a[rows, kron.indices.long()] = 1.0
+    want = torch.diagonal(a @ a @ a) / 2  # closed walks of length 3 through v, each triangle counted twice
+    assert torch.equal(counts.double(), want) and all_triangles == int(want.sum().item())
 
 
 _MST_SNIPPET = """
