@@ -128,7 +128,18 @@ struct enactor_t : gunrock::enactor_t<problem_t> {
       return float(thread::load<thread::cache_t::global>(&distances[v]));
     };
     if constexpr (near_far) {
-      near_far_stats = operators::advance::execute_near_far(G, E, relax, tentative, delta, context);
+      // the same relaxation split at the atomic (advance::two_phase): the kernel keeps a lane's edges in flight together
+      auto relax_issue = [distances] __host__ __device__(vertex_t const& source, vertex_t const& neighbor,
+                                                         edge_t const& edge, weight_t const& weight) -> float2 {
+        const weight_t candidate = thread::load<thread::cache_t::global>(&distances[source]) + weight;
+        return make_float2(float(candidate), float(math::atomic::min(&distances[neighbor], candidate)));
+      };
+      auto relax_resolve = [] __host__ __device__(float2 const& token) -> bool { return token.x < token.y; };
+      (void)relax;
+      // (a per-source prologue — two_phase(prepare, issue, resolve), one label read per vertex — measured the same
+      // time on the 4900^2 grid but 30 % more relaxations, because a staler source label is used for later edges)
+      near_far_stats = operators::advance::execute_near_far(
+          G, E, operators::advance::two_phase(relax_issue, relax_resolve), tentative, delta, context);
       this->iteration += near_far_stats.levels > 0 ? near_far_stats.levels - 1 : 0;  // enact() adds the last one
       (void)visited;
       (void)iteration;

@@ -463,6 +463,18 @@ kernels::directional_operator_t<push_t, pull_t> directional(push_t push, pull_t 
   return kernels::directional_operator_t<push_t, pull_t>{push, pull};
 }
 
+/// Splits an operator into issue / resolve halves so batched kernels can overlap the atomics of several edges
+/// (see kernels::two_phase_operator_t).
+template <typename issue_t, typename resolve_t>
+kernels::two_phase_operator_t<issue_t, resolve_t> two_phase(issue_t issue, resolve_t resolve) {
+  return kernels::two_phase_operator_t<issue_t, resolve_t>{issue, resolve};
+}
+
+template <typename prepare_t, typename issue_t, typename resolve_t>
+kernels::staged_operator_t<prepare_t, issue_t, resolve_t> two_phase(prepare_t prepare, issue_t issue, resolve_t resolve) {
+  return kernels::staged_operator_t<prepare_t, issue_t, resolve_t>{prepare, issue, resolve};
+}
+
 /**
  * @brief Explicit-buffers form (reference advance.hxx:91-129; used by e.g. bc.hxx:140-146).
  */

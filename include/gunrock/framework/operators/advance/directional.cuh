@@ -45,6 +45,53 @@ __device__ __forceinline__ bool call_pull(operator_t& op, vertex_t src, vertex_t
     return op(src, dst, edge, weight);
 }
 
+/**
+ * @brief Two-phase form of an advance operator for latency-bound traversals (advance::two_phase(issue, resolve)).
+ * `issue(src, dst, e, w)` starts the update — typically the atomic — and returns a token (e.g. candidate and old
+ * value); `resolve(token)` turns it into the operator's bool. Kernels that keep several edges per lane in flight
+ * (near_far.cuh) call every issue of a batch before the first resolve, so the atomics' round trips overlap; with a
+ * plain operator the compare that consumes one atomic's result sits in front of the next atomic and the in-order
+ * warp pays one full L2 round trip per edge (measured: ~1 us each, four in a row per lane on the 2-D grid).
+ * Used as a plain operator it is resolve(issue(...)).
+ */
+template <typename issue_t, typename resolve_t>
+struct two_phase_operator_t {
+  issue_t issue;
+  resolve_t resolve;
+  template <typename V, typename E, typename W>
+  __host__ __device__ __forceinline__ bool operator()(V& src, V& dst, E& edge, W& weight) const {
+    return resolve(issue(src, dst, edge, weight));
+  }
+};
+
+/**
+ * @brief Two-phase operator with a per-SOURCE prologue (advance::two_phase(prepare, issue, resolve)):
+ * `prepare(src)` runs once per frontier vertex and its result (e.g. the source's tentative distance) is handed to
+ * every `issue(state, src, dst, e, w)` of that vertex — one label read per vertex instead of one per edge, and no
+ * load in front of each atomic.
+ */
+template <typename prepare_t, typename issue_t, typename resolve_t>
+struct staged_operator_t {
+  prepare_t prepare;
+  issue_t issue;
+  resolve_t resolve;
+  template <typename V, typename E, typename W>
+  __host__ __device__ __forceinline__ bool operator()(V& src, V& dst, E& edge, W& weight) const {
+    return resolve(issue(prepare(src), src, dst, edge, weight));
+  }
+};
+
+template <typename T, typename = void>
+struct has_prepare : std::false_type {};
+template <typename T>
+struct has_prepare<T, std::void_t<decltype(std::declval<T>().prepare)>> : std::true_type {};
+
+template <typename T, typename = void>
+struct has_two_phase : std::false_type {};
+template <typename T>
+struct has_two_phase<T, std::void_t<decltype(std::declval<T>().issue), decltype(std::declval<T>().resolve)>>
+    : std::true_type {};
+
 }  // namespace kernels
 }  // namespace advance
 }  // namespace operators

@@ -31,6 +31,7 @@
 #include <cooperative_groups.h>
 
 #include <gunrock/b200/warp.cuh>
+#include <gunrock/framework/operators/advance/directional.cuh>
 #include <gunrock/cuda/context.hxx>
 #include <gunrock/graph/graph.hxx>
 
@@ -84,18 +85,22 @@ __device__ __forceinline__ void near_far_expand_level(
   // together, and the whole warp claims its queue slots with ONE distributed-shared-memory atomic per queue.
   auto route4 = [&](const bool (&improved)[4], const vertex_t (&u)[4]) {  // called by all 32 lanes
     float pri[4];
+    int previous[4];
     bool to_near[4], to_far[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) pri[j] = improved[j] ? float(priority(u[j])) : 0.f;
+    // all exchanges of the batch are issued before the first result is looked at (in-order issue: a compare in
+    // between would make the warp wait for each round trip in turn)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      to_near[j] = to_far[j] = false;
-      if (improved[j]) {
-        if (pri[j] < threshold)
-          to_near[j] = atomicExch(queue_stamp + u[j], next_level) != next_level;
-        else
-          to_far[j] = atomicExch(far_flag + u[j], 1) == 0;
-      }
+      previous[j] = 0;
+      if (improved[j])
+        previous[j] = pri[j] < threshold ? atomicExch(queue_stamp + u[j], next_level) : atomicExch(far_flag + u[j], 1);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      to_near[j] = improved[j] && pri[j] < threshold && previous[j] != next_level;
+      to_far[j] = improved[j] && !(pri[j] < threshold) && previous[j] == 0;
     }
     unsigned near_votes[4], far_votes[4], n_near = 0, n_far_new = 0;
 #pragma unroll
@@ -125,6 +130,38 @@ __device__ __forceinline__ void near_far_expand_level(
       }
       base_near += __popc(near_votes[j]);
       base_far += __popc(far_votes[j]);
+    }
+  };
+
+  // Runs the operator on the (up to) 4 live edges of a lane. A two-phase operator has all its issues (atomics) in
+  // flight before the first resolve; a plain operator is simply called edge by edge.
+  auto apply4 = [&](vertex_t source, const bool (&live)[4], vertex_t (&u)[4], edge_t (&edge)[4], weight_t (&w)[4],
+                    bool (&improved)[4]) {
+    if constexpr (has_two_phase<operator_t>::value && has_prepare<operator_t>::value) {
+      vertex_t s = source;
+      const auto state = op.prepare(s);  // once per source (and batch): e.g. its tentative distance
+      using token_t = decltype(op.issue(state, s, u[0], edge[0], w[0]));
+      token_t token[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (live[j]) token[j] = op.issue(state, s, u[j], edge[j], w[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) improved[j] = live[j] && op.resolve(token[j]);
+    } else if constexpr (has_two_phase<operator_t>::value) {
+      vertex_t s = source;
+      using token_t = decltype(op.issue(s, u[0], edge[0], w[0]));
+      token_t token[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (live[j]) token[j] = op.issue(s, u[j], edge[j], w[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) improved[j] = live[j] && op.resolve(token[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        vertex_t s = source;
+        improved[j] = live[j] && op(s, u[j], edge[j], w[j]);
+      }
     }
   };
 
@@ -158,15 +195,13 @@ __device__ __forceinline__ void near_far_expand_level(
             if (A.values) w[j] = __ldg(A.values + edge[j]);
           }
         }
+        bool live[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          improved[j] = false;
-          if (edge[j] < e_end) {
-            vertex_t s = src;
-            ++my_relax;
-            improved[j] = op(s, u[j], edge[j], w[j]);
-          }
+          live[j] = edge[j] < e_end;
+          my_relax += live[j];
         }
+        apply4(src, live, u, edge, w, improved);
         route4(improved, u);
       }
     }
@@ -189,30 +224,36 @@ __device__ __forceinline__ void near_far_expand_level(
           if (A.values) w[j] = __ldg(A.values + edge[j]);
         }
       }
+      bool live[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        improved[j] = false;
-        if (k0 + edge_t(j) < short_deg) {
-          vertex_t s = v;
-          ++my_relax;
-          improved[j] = op(s, u[j], edge[j], w[j]);
-        }
+        live[j] = k0 + edge_t(j) < short_deg;
+        my_relax += live[j];
       }
+      apply4(v, live, u, edge, w, improved);
       route4(improved, u);
     }
   }
 }
 
-template <typename vertex_t, typename edge_t, typename weight_t, typename operator_t, typename priority_t>
-__global__ void __launch_bounds__(256, 2)
-    near_far_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op, priority_t priority,
-                    float delta, vertex_t* near0, vertex_t* near1, vertex_t* far0, vertex_t* far1, int* queue_stamp,
-                    int* far_flag, near_far_state_t* state, unsigned long long capacity, int max_levels,
-                    unsigned long long shrink_limit) {
-  // shrink_limit > 0: return (near_far_shrank) as soon as a near level has at most that many vertices, so the host
-  // can continue in near_far_cluster_kernel, whose level barrier is ~10x cheaper
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+/**
+ * @brief The whole traversal, shared by the two kernels below; `sync()` is the device-wide (cooperative grid) or the
+ * cluster-wide (hardware barrier.cluster) barrier — both order global memory among the threads they join.
+ * shrink_limit > 0: return near_far_shrank as soon as a near level holds at most that many vertices (grid-wide
+ * kernel: the host continues in the cluster kernel, whose barrier is several times cheaper). grow_limit > 0: return
+ * near_far_grew when a near level exceeds it or the far pile exceeds 64 x it (cluster kernel -> grid-wide kernel).
+ * Queue lengths, threshold and selectors live in `state` (global memory, L2): a first version of the cluster kernel
+ * kept them in the leader CTA's shared memory and appended through distributed-shared-memory atomics — ~600 remote
+ * atomics per level serialised on one SM's shared-memory port and cost more than the barrier saved.
+ */
+template <typename vertex_t, typename edge_t, typename weight_t, typename operator_t, typename priority_t,
+          typename sync_t>
+__device__ __forceinline__ void near_far_run(const graph::adjacency_t<vertex_t, edge_t, weight_t>& A, operator_t& op,
+                                             priority_t& priority, float delta, vertex_t* near0, vertex_t* near1,
+                                             vertex_t* far0, vertex_t* far1, int* queue_stamp, int* far_flag,
+                                             near_far_state_t* state, unsigned long long capacity, int max_levels,
+                                             unsigned long long shrink_limit, unsigned long long grow_limit,
+                                             sync_t sync) {
   volatile near_far_state_t* st = state;
   const unsigned lane = b200::lane_id();
   const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -223,148 +264,9 @@ __global__ void __launch_bounds__(256, 2)
   int level = st->level;
   int reason = near_far_done;
   bool stop = false;
-
-  while (!stop) {
-    // ---------------------------- near levels: one grid barrier each ----------------------------
-    for (;;) {
-      const unsigned long long n_in = st->near_count[level % 3];
-      if (n_in == 0) break;
-      if (level >= max_levels) {
-        stop = true;
-        break;
-      }
-      if (n_in <= shrink_limit) {  // uniform: every thread read the same value after the barrier
-        stop = true;
-        reason = near_far_shrank;
-        break;
-      }
-      const vertex_t* q_in = near_q[level & 1];
-      vertex_t* q_out = near_q[(level + 1) & 1];
-      unsigned long long* out_count = &state->near_count[(level + 1) % 3];
-      const float threshold = st->threshold;
-      const int fsel = st->far_selector;
-      vertex_t* far_out = far_q[fsel];
-      unsigned long long* far_count = &state->far_count[fsel];
-      const int next_level = level + 1;
-      if (tid == 0) st->near_count[(level + 2) % 3] = 0;  // consumed a level ago; the next level appends to it
-
-      bool overflowed = false;
-      near_far_expand_level(A, op, priority, q_in, n_in, q_out, out_count, far_out, far_count, threshold, next_level,
-                            queue_stamp, far_flag, capacity, tid, threads, my_relax, overflowed);
-      if (overflowed) state->overflow = 1;
-      grid.sync();
-      ++level;
-    }
-    if (stop) break;
-
-    // ---------------------------- far pile: raise the threshold, split ----------------------------
-    const int fsel = st->far_selector;
-    const unsigned long long n_far = st->far_count[fsel];
-    if (n_far == 0) break;
-    const vertex_t* far_in = far_q[fsel];
-    vertex_t* far_keep = far_q[fsel ^ 1];
-    {
-      unsigned lowest = near_far_inf_bits;
-      for (unsigned long long i = tid; i < n_far; i += threads) {
-        const unsigned bits = __float_as_uint(float(priority(far_in[i])));
-        lowest = bits < lowest ? bits : lowest;
-      }
-      for (int d = 16; d > 0; d >>= 1) {
-        const unsigned other = __shfl_xor_sync(b200::full_mask, lowest, d);
-        lowest = other < lowest ? other : lowest;
-      }
-      if (lane == 0 && lowest != near_far_inf_bits) atomicMin(&state->far_min_bits, lowest);
-    }
-    grid.sync();
-    const float old_threshold = st->threshold;
-    const float far_min = __uint_as_float(st->far_min_bits);
-    float new_threshold = (floorf(far_min / delta) + 1.0f) * delta;
-    if (!(new_threshold > old_threshold)) new_threshold = old_threshold + delta;
-    // strict progress past the smallest pending key: both forms above can round to <= far_min once keys exceed
-    // ~2^24 * delta, and a far pile that never drains would spin this persistent kernel for ever
-    if (!(new_threshold > far_min)) new_threshold = nextafterf(far_min, __int_as_float(0x7f800000));
-    {
-      vertex_t* q_in = near_q[level & 1];  // promoted vertices become the input of the next near level
-      unsigned long long* in_count = &state->near_count[level % 3];
-      unsigned long long* keep_count = &state->far_count[fsel ^ 1];
-      for (unsigned long long i = tid; i < n_far; i += threads) {
-        const vertex_t u = far_in[i];
-        const float p = float(priority(u));
-        if (p < old_threshold) {
-          far_flag[u] = 0;  // stale: it was expanded from `near` when it dropped below the old threshold
-        } else if (p < new_threshold) {
-          far_flag[u] = 0;
-          if (atomicExch(queue_stamp + u, level) != level) {
-            const unsigned long long at = atomicAdd(in_count, 1ull);
-            if (at < capacity) q_in[at] = u; else state->overflow = 1;
-          }
-        } else {
-          const unsigned long long at = atomicAdd(keep_count, 1ull);
-          if (at < capacity) far_keep[at] = u; else state->overflow = 1;
-        }
-      }
-    }
-    grid.sync();
-    if (tid == 0) {
-      st->threshold = new_threshold;
-      st->far_count[fsel] = 0;
-      st->far_selector = fsel ^ 1;
-      st->far_min_bits = near_far_inf_bits;
-      st->splits = st->splits + 1;
-    }
-    grid.sync();
-  }
-
-  my_relax = b200::warp_sum(my_relax);
-  if (lane == 0 && my_relax) atomicAdd(&state->relaxations, my_relax);
-  if (tid == 0) {
-    st->levels = level;
-    st->level = level;
-    st->exit_reason = reason;
-  }
-}
-
-/**
- * @brief The same traversal run by ONE thread-block cluster (8 or 16 CTAs x 1024 threads on neighbouring SMs).
- *
- * Why. On the 4900 x 4900 grid a near level holds at most ~10 K vertices and there are ~12.6 K levels; the grid-wide
- * kernel spends ~15 us per level, almost all of it in the 148-CTA cooperative barrier and in dependent L2 round
- * trips on the queue counters. A cluster gives (a) a HARDWARE barrier (barrier.cluster, ~0.2 us instead of ~3 us),
- * (b) the queue counters and the threshold in the leader CTA's shared memory, reached by the other CTAs through
- * distributed shared memory (~215 cycles, atomics included) instead of L2 atomics, and 16 K threads are still one
- * thread per relaxation at these frontier sizes. Queues, stamps and the user's data stay in global memory (L2).
- * Appends are warp-aggregated (ballot + one DSMEM atomic per warp), so the leader's shared-memory port sees at most
- * a few hundred atomics per level. When a level or the far pile outgrows `grow_limit` the kernel writes its state
- * back and returns near_far_grew; execute_near_far continues with the grid-wide kernel.
- */
-template <typename vertex_t, typename edge_t, typename weight_t, typename operator_t, typename priority_t>
-__global__ void __launch_bounds__(1024, 1)
-    near_far_cluster_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op, priority_t priority,
-                            float delta, vertex_t* near0, vertex_t* near1, vertex_t* far0, vertex_t* far1,
-                            int* queue_stamp, int* far_flag, near_far_state_t* state, unsigned long long capacity,
-                            int max_levels, unsigned long long grow_limit) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  __shared__ near_far_state_t s_ctl;          // live copy; only the leader's is used
-  __shared__ unsigned long long s_in[4];      // per-CTA broadcast of the level's inputs
-  near_far_state_t* ctl = cluster.map_shared_rank(&s_ctl, 0);
-  const unsigned lane = b200::lane_id();
-  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long threads = (unsigned long long)gridDim.x * blockDim.x;
-  const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
-  vertex_t* near_q[2] = {near0, near1};
-  vertex_t* far_q[2] = {far0, far1};
-  if (leader) s_ctl = *state;
-  cluster.sync();
-  unsigned long long my_relax = 0;
-  int level = 0;
-  if (threadIdx.x == 0) s_in[0] = (unsigned long long)ctl->level;
-  __syncthreads();
-  level = int(s_in[0]);
-  int reason = near_far_done;
   bool overflowed = false;
 
-  // warp-aggregated append to a queue whose length lives in distributed shared memory
+  // warp-aggregated append (one atomic per warp and call)
   auto append = [&](bool keep, vertex_t value, vertex_t* queue, unsigned long long* count) {
     const unsigned votes = __ballot_sync(b200::full_mask, keep);
     if (votes == 0) return;
@@ -378,43 +280,46 @@ __global__ void __launch_bounds__(1024, 1)
     }
   };
 
-  for (;;) {
-    __syncthreads();  // s_in reuse
-    if (threadIdx.x == 0) {
-      s_in[0] = ctl->near_count[level % 3];
-      s_in[1] = (unsigned long long)__float_as_uint(ctl->threshold);
-      s_in[2] = (unsigned long long)ctl->far_selector;
-      s_in[3] = ctl->far_count[ctl->far_selector];
-    }
-    __syncthreads();
-    const unsigned long long n_in = s_in[0];
-    const float threshold = __uint_as_float(unsigned(s_in[1]));
-    const int fsel = int(s_in[2]);
-    const unsigned long long n_far = s_in[3];
-    if (n_in > 0) {
-      // ------------------------------ one near level, one cluster barrier ------------------------------
-      if (level >= max_levels) break;
-      if (n_in > grow_limit) {
+  while (!stop) {
+    // ---------------------------- near levels: one barrier each ----------------------------
+    for (;;) {
+      const unsigned long long n_in = st->near_count[level % 3];
+      if (n_in == 0) break;
+      if (level >= max_levels) {
+        stop = true;
+        break;
+      }
+      if (n_in <= shrink_limit) {  // uniform: every thread reads the same value after the barrier
+        stop = true;
+        reason = near_far_shrank;
+        break;
+      }
+      if (grow_limit && n_in > grow_limit) {
+        stop = true;
         reason = near_far_grew;
         break;
       }
       const vertex_t* q_in = near_q[level & 1];
       vertex_t* q_out = near_q[(level + 1) & 1];
-      unsigned long long* out_count = &ctl->near_count[(level + 1) % 3];
-      unsigned long long* far_count = &ctl->far_count[fsel];
+      unsigned long long* out_count = &state->near_count[(level + 1) % 3];
+      const float threshold = st->threshold;
+      const int fsel = st->far_selector;
       vertex_t* far_out = far_q[fsel];
+      unsigned long long* far_count = &state->far_count[fsel];
       const int next_level = level + 1;
-      if (leader) s_ctl.near_count[(level + 2) % 3] = 0;  // read a level ago, appended to a level from now
-
+      if (tid == 0) st->near_count[(level + 2) % 3] = 0;  // consumed a level ago; the next level appends to it
       near_far_expand_level(A, op, priority, q_in, n_in, q_out, out_count, far_out, far_count, threshold, next_level,
                             queue_stamp, far_flag, capacity, tid, threads, my_relax, overflowed);
-      cluster.sync();
+      sync();
       ++level;
-      continue;
     }
-    // ------------------------------ far pile: raise the threshold, split ------------------------------
+    if (stop) break;
+
+    // ---------------------------- far pile: raise the threshold, split ----------------------------
+    const int fsel = st->far_selector;
+    const unsigned long long n_far = st->far_count[fsel];
     if (n_far == 0) break;
-    if (n_far > 64 * grow_limit) {
+    if (grow_limit && n_far > 64 * grow_limit) {
       reason = near_far_grew;
       break;
     }
@@ -430,20 +335,20 @@ __global__ void __launch_bounds__(1024, 1)
         const unsigned other = __shfl_xor_sync(b200::full_mask, lowest, d);
         lowest = other < lowest ? other : lowest;
       }
-      if (lane == 0 && lowest != near_far_inf_bits) atomicMin(&ctl->far_min_bits, lowest);
+      if (lane == 0 && lowest != near_far_inf_bits) atomicMin(&state->far_min_bits, lowest);
     }
-    cluster.sync();
-    if (threadIdx.x == 0) s_in[0] = (unsigned long long)ctl->far_min_bits;
-    __syncthreads();
-    const float far_min = __uint_as_float(unsigned(s_in[0]));
-    const float old_threshold = threshold;
+    sync();
+    const float old_threshold = st->threshold;
+    const float far_min = __uint_as_float(st->far_min_bits);
     float new_threshold = (floorf(far_min / delta) + 1.0f) * delta;
     if (!(new_threshold > old_threshold)) new_threshold = old_threshold + delta;
+    // strict progress past the smallest pending key: both forms above can round to <= far_min once keys exceed
+    // ~2^24 * delta, and a far pile that never drains would spin this persistent kernel for ever
     if (!(new_threshold > far_min)) new_threshold = nextafterf(far_min, __int_as_float(0x7f800000));
     {
       vertex_t* q_in = near_q[level & 1];  // promoted vertices become the input of the next near level
-      unsigned long long* in_count = &ctl->near_count[level % 3];
-      unsigned long long* keep_count = &ctl->far_count[fsel ^ 1];
+      unsigned long long* in_count = &state->near_count[level % 3];
+      unsigned long long* keep_count = &state->far_count[fsel ^ 1];
       for (unsigned long long base = (tid >> 5) << 5; base < n_far; base += threads) {
         const unsigned long long i = base + lane;
         bool promote = false, keep = false;
@@ -464,27 +369,54 @@ __global__ void __launch_bounds__(1024, 1)
         append(keep, u, far_keep, keep_count);
       }
     }
-    cluster.sync();
-    if (leader) {
-      s_ctl.threshold = new_threshold;
-      s_ctl.far_count[fsel] = 0;
-      s_ctl.far_selector = fsel ^ 1;
-      s_ctl.far_min_bits = near_far_inf_bits;
-      s_ctl.splits = s_ctl.splits + 1;
+    sync();
+    if (tid == 0) {
+      st->threshold = new_threshold;
+      st->far_count[fsel] = 0;
+      st->far_selector = fsel ^ 1;
+      st->far_min_bits = near_far_inf_bits;
+      st->splits = st->splits + 1;
     }
-    cluster.sync();
+    sync();
   }
 
   my_relax = b200::warp_sum(my_relax);
-  if (lane == 0 && my_relax) atomicAdd(&ctl->relaxations, my_relax);
-  if (__syncthreads_or(overflowed) && threadIdx.x == 0) ctl->overflow = 1;
-  cluster.sync();
-  if (leader) {
-    s_ctl.levels = level;
-    s_ctl.level = level;
-    s_ctl.exit_reason = reason;
-    *state = s_ctl;
+  if (lane == 0 && my_relax) atomicAdd(&state->relaxations, my_relax);
+  if (overflowed) state->overflow = 1;
+  if (tid == 0) {
+    st->levels = level;
+    st->level = level;
+    st->exit_reason = reason;
   }
+}
+
+/// Grid-wide form: cooperative launch, one CTA of 256 threads per SM (knob), barrier = cooperative-groups grid sync.
+template <typename vertex_t, typename edge_t, typename weight_t, typename operator_t, typename priority_t>
+__global__ void __launch_bounds__(256, 2)
+    near_far_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op, priority_t priority,
+                    float delta, vertex_t* near0, vertex_t* near1, vertex_t* far0, vertex_t* far1, int* queue_stamp,
+                    int* far_flag, near_far_state_t* state, unsigned long long capacity, int max_levels,
+                    unsigned long long shrink_limit) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  near_far_run(A, op, priority, delta, near0, near1, far0, far1, queue_stamp, far_flag, state, capacity, max_levels,
+               shrink_limit, 0ull, [&]() { grid.sync(); });
+}
+
+/**
+ * @brief The same traversal run by ONE thread-block cluster (8 or 16 CTAs x 1024 threads on neighbouring SMs), for
+ * levels of at most a few ten thousand vertices (the 4900 x 4900 grid never has more than ~10 K in a level, over
+ * ~12.6 K levels): 16 K threads are still a thread per queued vertex there, and the level barrier is the hardware
+ * barrier.cluster instead of a 148-CTA cooperative grid sync.
+ */
+template <typename vertex_t, typename edge_t, typename weight_t, typename operator_t, typename priority_t>
+__global__ void __launch_bounds__(1024, 1)
+    near_far_cluster_kernel(const graph::adjacency_t<vertex_t, edge_t, weight_t> A, operator_t op, priority_t priority,
+                            float delta, vertex_t* near0, vertex_t* near1, vertex_t* far0, vertex_t* far1,
+                            int* queue_stamp, int* far_flag, near_far_state_t* state, unsigned long long capacity,
+                            int max_levels, unsigned long long grow_limit) {
+  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+  near_far_run(A, op, priority, delta, near0, near1, far0, far1, queue_stamp, far_flag, state, capacity, max_levels,
+               0ull, grow_limit, [&]() { cluster.sync(); });
 }
 
 }  // namespace kernels
@@ -495,9 +427,14 @@ inline int& near_far_ctas_per_sm() {
   return ctas;
 }
 
-/// Development knob (ess_tune "near_far_cluster"): run small levels in one thread-block cluster (default on).
+/// Knob (ess_tune "near_far_cluster"): run levels of at most 64 K vertices in ONE thread-block cluster (hardware
+/// barrier.cluster) and hand larger ones to the grid-wide kernel. Default OFF: on BASELINE config 3 (4900^2 grid,
+/// ~10 K vertices per level) the cluster kernel measured 11.9 us per level against 9.25 us for the grid-wide kernel
+/// (profiles/r02i_probe_grid.log): a level issues ~80 K global atomics (label min + stamp exchange), and 16 SMs'
+/// load/store units take longer to issue them than 148 SMs take to cross a cooperative grid barrier. Both paths
+/// stay tested (test_sssp_near_far_cluster_and_grid_kernels_agree).
 inline int& near_far_cluster_enabled() {
-  static int enabled = 1;
+  static int enabled = 0;
   return enabled;
 }
 

@@ -183,7 +183,7 @@ def test_sssp_near_far_cluster_and_grid_kernels_agree(ctx, cluster):
         dist, info = ess.sssp_near_far(ctx, ess.Graph(csr), s)
         assert np.array_equal(dist.cpu().numpy(), oracle.sssp(off, col, val, s))
     finally:
-        ess.tune("near_far_cluster", 1)
+        ess.tune("near_far_cluster", 0)
 
 
 def test_sssp_thresholds_make_progress_on_extreme_weight_ranges(ctx):
