@@ -175,12 +175,23 @@ int partition_step(ess_context_t ctx, graph_t& G, int64_t row_begin, int64_t n_g
     if (!(visited[u >> 5] & bit) && !(candidate[u >> 5] & bit)) atomicOr(candidate + (u >> 5), bit);
     return false;
   };
+  // owner-only visited set (peer-memory driver): every neighbour is a candidate, its owner filters (absorb_kernel)
+  auto op_unfiltered = [candidate] __device__(int32_t const& src, int32_t const& nbr, edge_t const& e,
+                                              float const& w) -> bool {
+    const unsigned u = unsigned(nbr), bit = 1u << (u & 31u);
+    if (!(candidate[u >> 5] & bit)) atomicOr(candidate + (u >> 5), bit);
+    return false;
+  };
   using namespace operators;
   auto& scratch = c->scratch();
   const bool was_async = scratch.async_when_no_output;
   scratch.async_when_no_output = true;
-  advance::execute<load_balance_t::merge_path, advance_direction_t::forward, advance_io_type_t::vertices,
-                   advance_io_type_t::none>(G, op, &in, &out, segments, *ctx->ctx);
+  if (visited)
+    advance::execute<load_balance_t::merge_path, advance_direction_t::forward, advance_io_type_t::vertices,
+                     advance_io_type_t::none>(G, op, &in, &out, segments, *ctx->ctx);
+  else
+    advance::execute<load_balance_t::merge_path, advance_direction_t::forward, advance_io_type_t::vertices,
+                     advance_io_type_t::none>(G, op_unfiltered, &in, &out, segments, *ctx->ctx);
   scratch.async_when_no_output = was_async;
   return 0;
 }
@@ -533,6 +544,59 @@ static __global__ void peer_signal_kernel(peers_t peers, int world, int rank, st
   }
 }
 
+/// all_gather of the level's result, second form: the slice goes into row `rank` of the peers' BITS area (rows of
+/// exactly slice_words, so the area IS the replicated next-frontier bitmap — no unpacking pass) and the two Beamer
+/// counters into row `rank` of their COUNTS area. Zero words / counters are skipped (receivers keep both all-zero).
+static __global__ void __launch_bounds__(256)
+    peer_publish_level_kernel(const unsigned* __restrict__ slice, const unsigned* __restrict__ counters4, peers_t peers,
+                              int world, int rank, unsigned slice_words, std::size_t bits_off, std::size_t cnt_off,
+                              std::size_t flag_off, unsigned epoch, unsigned* done) {
+  const std::size_t pairs = slice_words / 2, total = pairs * world;
+  const uint2* in = reinterpret_cast<const uint2*>(slice);
+  for (std::size_t i = std::size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += std::size_t(gridDim.x) * blockDim.x) {
+    const int p = int(i / pairs);
+    const std::size_t k = i - std::size_t(p) * pairs;
+    const uint2 v = in[k];
+    if (v.x | v.y) reinterpret_cast<uint2*>(peers.base[p] + bits_off + std::size_t(rank) * slice_words)[k] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < unsigned(world) * 4u) {
+    const int p = threadIdx.x >> 2, k = threadIdx.x & 3;
+    const unsigned v = counters4[k];
+    if (v) peers.base[p][cnt_off + std::size_t(rank) * 4 + k] = v;
+  }
+  raise_flags_when_grid_done(peers, world, rank, flag_off, epoch, done);
+}
+
+/// Stream-side wait for every peer's level data, then the level's ONE host hand-off: the P x 2 counters go to
+/// mapped pinned host memory (and are cleared in the window), followed by the sequence word the host spins on —
+/// a PCIe write instead of cudaMemcpyAsync(D2H) + cudaStreamSynchronize.
+static __global__ void peer_wait_publish_kernel(const unsigned* flags, int world, unsigned epoch, unsigned* timed_out,
+                                                unsigned* cnt_area, volatile long long* host_counts,
+                                                unsigned long long sequence) {
+  if (threadIdx.x < unsigned(world)) {
+    const volatile unsigned* flag = flags + threadIdx.x;
+    const long long start = clock64();
+    while (int(*flag - epoch) < 0) {
+      if (clock64() - start > 8000000000LL) {
+        *timed_out = 1u + threadIdx.x;
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < unsigned(world) * 2u) {
+    volatile long long* cell = reinterpret_cast<volatile long long*>(cnt_area) + threadIdx.x;
+    host_counts[threadIdx.x] = *cell;
+    *cell = 0;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) host_counts[2 * max_peers] = (long long)sequence;
+}
+
 struct replicas_t {
   const float* value[max_peers];     ///< every rank's full-length replica of tentative distances
   const unsigned* dirty[max_peers];  ///< its per-1024-entry dirty words
@@ -618,6 +682,9 @@ struct ess_dist_s {
   peers_t peers{};
   bool peer_ready = false;
   std::size_t inbox_off = 0, gather_off[2] = {0, 0}, flag_off[2] = {0, 0};
+  std::size_t bits_off[2] = {0, 0}, cnt_off[2] = {0, 0};  // replicated next-frontier bitmap + counters, by parity
+  long long* level_counts = nullptr;   // mapped pinned: [2 * max_peers] counters + sequence word
+  unsigned long long level_sequence = 0;
   unsigned epoch = 0;
   // SSSP over peer memory: replica + dirty words in one IPC-mapped allocation per rank
   float* replica_window = nullptr;
@@ -635,6 +702,7 @@ struct ess_dist_s {
     if (window) cudaFree(window);
     if (done_counter) cudaFree(done_counter);
     if (timed_out) cudaFreeHost(timed_out);
+    if (level_counts) cudaFreeHost(level_counts);
     if (counts_host) cudaFreeHost(counts_host);
     if (comm && nccl().CommDestroy) nccl().CommDestroy(comm);
   }
@@ -731,14 +799,21 @@ int ess_dist_create(ess_context_t ctx, ess_graph_t g, int rank, int world, int64
     d->gather_off[1] = d->gather_off[0] + row * world;
     d->flag_off[0] = d->gather_off[1] + row * world;
     d->flag_off[1] = d->flag_off[0] + 32;
-    const std::size_t window_words = d->flag_off[1] + 32;
+    d->bits_off[0] = d->flag_off[1] + 32;
+    d->bits_off[1] = d->bits_off[0] + std::size_t(d->words);
+    d->cnt_off[0] = d->bits_off[1] + std::size_t(d->words);
+    d->cnt_off[1] = d->cnt_off[0] + 4 * std::size_t(max_peers);
+    const std::size_t window_words = d->cnt_off[1] + 4 * std::size_t(max_peers);
     cudaIpcMemHandle_t mine;
     bool ok = cudaMalloc(&d->window, window_words * sizeof(unsigned)) == cudaSuccess &&
               cudaMemsetAsync(d->window, 0, window_words * sizeof(unsigned), stream) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine, d->window) == cudaSuccess &&
               cudaMalloc(&d->done_counter, sizeof(unsigned)) == cudaSuccess &&
               cudaMemsetAsync(d->done_counter, 0, sizeof(unsigned), stream) == cudaSuccess &&
-              cudaHostAlloc(&d->timed_out, sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess;
+              cudaHostAlloc(&d->timed_out, sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostAlloc(&d->level_counts, (2 * max_peers + 1) * sizeof(long long), cudaHostAllocMapped) ==
+                  cudaSuccess;
+    if (d->level_counts) std::memset(d->level_counts, 0, (2 * max_peers + 1) * sizeof(long long));
     memory::device_array_t<unsigned char> handles(std::size_t(world + 1) * sizeof(cudaIpcMemHandle_t));
     std::vector<cudaIpcMemHandle_t> all(world);
     if (!ok) std::memset(&mine, 0, sizeof(mine));
@@ -914,6 +989,9 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
   long long exchanged = 0;
 
   const bool peer = d->peer_ready && ess::dist_peer_exchange() != 0;
+  // replicated frontier bitmap the level kernels read: the seed array at level 1, then (peer-memory driver) the
+  // window area the previous level's slices landed in
+  unsigned* cur_frontier = d->frontier_bits.data();
   // ess_tune("dist_trace", 1): CUDA events between the phases of every level, summed and printed by rank 0
   const bool trace = ess::dist_trace() != 0;
   static const char* phase_names[] = {"local(push|pull)", "candidates->owners", "absorb", "slice->all", "merge", "host"};
@@ -938,7 +1016,7 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
     if (pulling) {
       ++pulls;
       ESS_WITH_GRAPH(g, G, {
-        partition_pull(d->ctx, G, d->row_begin, level, d->frontier_bits.data(), d->visited_bits.data(), next_slice,
+        partition_pull(d->ctx, G, d->row_begin, level, cur_frontier, d->visited_bits.data(), next_slice,
                        d->depth_local.data(), reinterpret_cast<int64_t*>(counts));
       })
       list_is_current = false;
@@ -948,11 +1026,12 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
         auto& scratch = c->scratch();
         scratch.zero(stream);
         frontier::kernels::gather_bits_kernel<<<gcuda::persistent_grid(*c, (std::size_t(wper) + 255) / 256, 8), 256, 0,
-                                                stream>>>(d->frontier_bits.data() + first_word, std::size_t(wper),
+                                                stream>>>(cur_frontier + first_word, std::size_t(wper),
                                                           d->fresh_list.data(), scratch.d + scratch_t::out_count);
       }
       ESS_WITH_GRAPH(g, G, {
-        partition_step(d->ctx, G, d->row_begin, d->n_global, 0, d->frontier_bits.data(), d->visited_bits.data(),
+        // peer-memory driver: the visited set is owner-only (no replicated copy to pre-filter with)
+        partition_step(d->ctx, G, d->row_begin, d->n_global, 0, cur_frontier, peer ? nullptr : d->visited_bits.data(),
                        d->candidate_bits.data(), d->fresh_list.data(), my_count);
       })
       list_is_current = true;
@@ -987,27 +1066,51 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
                                                           peer);
     }
     if (!pulling) mark(2);
-    unsigned* gathered = d->recv.data();
-    if (peer) {  // the new frontier slice + counters land in every rank's gather area (double-buffered by epoch parity)
-      const std::size_t area = d->gather_off[epoch & 1];
-      peer_broadcast_kernel<<<gcuda::persistent_grid(*c, (std::size_t(wper + 4) / 2 * world + 255) / 256, 4), 256, 0,
-                              stream>>>(d->send.data(), d->peers, world, rank, wper + 4, area, d->flag_off[1], epoch,
-                                        d->done_counter);
-      peer_wait_kernel<<<1, 32, 0, stream>>>(d->window + d->flag_off[1], world, epoch, d->timed_out);
+    if (peer) {
+      // The new frontier slice lands in row `rank` of every rank's BITS area of this epoch's parity: once all flags
+      // are up that area IS the replicated next-frontier bitmap (no unpacking pass, no replicated visited set), and
+      // the counters reach the host through mapped memory (no D2H copy, no stream synchronisation).
+      // The other parity's area — the frontier this level just finished reading — is cleared first: peers write
+      // into it one level from now, only after they have seen the flag raised below (senders skip zero words).
+      const std::size_t bits = d->bits_off[epoch & 1], cnts = d->cnt_off[epoch & 1];
+      if (cur_frontier == d->window + d->bits_off[(epoch & 1) ^ 1])
+        cudaMemsetAsync(d->window + d->bits_off[(epoch & 1) ^ 1], 0, std::size_t(words) * sizeof(unsigned), stream);
+      peer_publish_level_kernel<<<gcuda::persistent_grid(*c, (std::size_t(wper) / 2 * world + 255) / 256, 4), 256, 0,
+                                  stream>>>(next_slice, d->send.data() + wper, d->peers, world, rank, wper, bits, cnts,
+                                            d->flag_off[1], epoch, d->done_counter);
+      mark(3);
+      const unsigned long long sequence = ++d->level_sequence;
+      peer_wait_publish_kernel<<<1, 32, 0, stream>>>(d->window + d->flag_off[1], world, epoch, d->timed_out,
+                                                     d->window + cnts, d->level_counts, sequence);
       c->profiler().launches_total += 2;
-      gathered = d->window + area;
+      mark(4);
+      mark(5);
+      volatile long long* seq = d->level_counts + 2 * max_peers;
+      for (unsigned spins = 0; (unsigned long long)*seq != sequence; ++spins) {
+        if ((spins & 0x3ff) == 0x3ff) {  // every ~1k polls make sure the stream is still healthy
+          cudaError_t st = cudaStreamQuery(stream);
+          if (st != cudaSuccess && st != cudaErrorNotReady) error::throw_if_exception(st, "dist bfs level");
+          if (st == cudaSuccess && (unsigned long long)*seq != sequence) {
+            error::throw_if_exception(cudaStreamSynchronize(stream), "dist bfs level");
+            if ((unsigned long long)*seq != sequence) error::throw_if_exception(cudaErrorUnknown, "level hand-off lost");
+          }
+        }
+      }
+      for (int p = 0; p < 2 * world; ++p) d->counts_host[p] = d->level_counts[p];
+      cur_frontier = d->window + bits;
+      exchanged += (long long)(world - 1) * (wper + 4) * 4;
     } else {
       nccl_check(api.AllGather(d->send.data(), d->recv.data(), wper + 4, ncclUint32, d->comm, stream), "allgather");
+      exchanged += (long long)(world - 1) * (wper + 4) * 4;
+      mark(3);
+      merge_gathered_kernel<<<gcuda::persistent_grid(*c, (std::size_t(words) + 255) / 256, 8), 256, 0, stream>>>(
+          d->recv.data(), world, wper, d->frontier_bits.data(), d->visited_bits.data(), d->counts_dev.data(), false);
+      mark(4);
+      cudaMemcpyAsync(d->counts_host, d->counts_dev.data(), 2 * std::size_t(world) * sizeof(long long),
+                      cudaMemcpyDeviceToHost, stream);
+      mark(5);
+      error::throw_if_exception(cudaStreamSynchronize(stream), "dist bfs level");  // the one host sync of the level
     }
-    exchanged += (long long)(world - 1) * (wper + 4) * 4;
-    mark(3);
-    merge_gathered_kernel<<<gcuda::persistent_grid(*c, (std::size_t(words) + 255) / 256, 8), 256, 0, stream>>>(
-        gathered, world, wper, d->frontier_bits.data(), d->visited_bits.data(), d->counts_dev.data(), peer);
-    mark(4);
-    cudaMemcpyAsync(d->counts_host, d->counts_dev.data(), 2 * std::size_t(world) * sizeof(long long),
-                    cudaMemcpyDeviceToHost, stream);
-    mark(5);
-    error::throw_if_exception(cudaStreamSynchronize(stream), "dist bfs level");  // the one host sync of the level
     if (peer && *d->timed_out) {
       const unsigned who = *d->timed_out - 1;
       *d->timed_out = 0;

@@ -7,7 +7,12 @@ rank advances next, so a rank may run arbitrarily far ahead of the others (only 
 collectives hold it back, exactly as on the device). The windows are modelled per (receiver, area, sender) cell:
 
     CLEAR --sender stores its non-zero words, then raises flag = epoch--> FULL(epoch)
-    FULL(epoch) --receiver's consuming kernel reads and zeroes it--> CLEAR
+    FULL(epoch) --receiver's consuming kernel reads and zeroes it--> CLEAR            (candidate inbox)
+    FULL(epoch) --read in place as the next level's frontier, then memset--> CLEAR    (next-frontier areas)
+
+The next-frontier areas are not unpacked: the area of epoch e IS the replicated frontier bitmap that level e+1's
+kernels read; the receiver clears it after those kernels and BEFORE it raises its own level-(e+1) flag, which is what
+every peer waits for before it writes that parity again (level e+2).
 
 Because senders skip zero words, a store into a cell that is not CLEAR would leave stale bits behind, and a consumer
 that finds anything but FULL(its own epoch) would read missing or future data: both are assertion failures here.
@@ -33,13 +38,18 @@ class Rank:
 
 
 def bfs_program(levels, first_epoch):
-    """Stream order of one rank for one BFS (capi_dist.cu, ess_dist_bfs): `levels` is a list of 'push' / 'pull'."""
+    """Stream order of one rank for one BFS (capi_dist.cu, ess_dist_bfs, peer-memory driver): `levels` is a list of
+    'push' / 'pull'. The last level of a run finds nothing, so its slices are empty (nothing is stored)."""
     ops = []
     for i, kind in enumerate(levels):
         epoch = first_epoch + i
+        if i > 0:
+            ops.append(("read_frontier", epoch - 1))   # this level's kernels read the area the previous level filled
         if kind == "push":
             ops += [("scatter", epoch), ("wait_a", epoch), ("absorb", epoch)]
-        ops += [("broadcast", epoch), ("wait_b", epoch), ("merge", epoch)]
+        if i > 0:
+            ops.append(("clear_frontier", epoch - 1))  # memset of that area, enqueued before the publish kernel
+        ops += [("broadcast_empty" if i == len(levels) - 1 else "broadcast", epoch), ("wait_b", epoch)]
     ops.append(("collective", first_epoch + len(levels)))  # the seed all_reduce of the next run / end of the run
     return ops
 
@@ -80,16 +90,18 @@ def run_bfs_model(world, runs, rng, gather_buffers=2):
             for s in range(world):
                 assert rk.inbox[s] == e, f"rank {rk.rank} absorbs epoch {rk.inbox[s]} from {s}, wants {e}"
                 rk.inbox[s] = CLEAR
-        elif op == "broadcast":
+        elif op in ("broadcast", "broadcast_empty"):
             for peer in ranks:
                 assert peer.gather[buf][rk.rank] is CLEAR, \
-                    f"rank {rk.rank} (epoch {e}) stores into gather[{buf}] of {peer.rank} before it was merged"
-                peer.gather[buf][rk.rank] = e
+                    f"rank {rk.rank} (epoch {e}) stores into area[{buf}] of {peer.rank} before it was cleared"
+                if op == "broadcast":
+                    peer.gather[buf][rk.rank] = e
                 peer.flag_b[rk.rank] = e
-        elif op == "merge":
+        elif op == "read_frontier":
             for s in range(world):
-                assert rk.gather[buf][s] == e, f"rank {rk.rank} merges epoch {rk.gather[buf][s]} from {s}, wants {e}"
-                rk.gather[buf][s] = CLEAR
+                assert rk.gather[buf][s] == e, f"rank {rk.rank} reads frontier epoch {rk.gather[buf][s]} from {s}, wants {e}"
+        elif op == "clear_frontier":
+            rk.gather[buf] = [CLEAR] * world
         rk.pc += 1
     for rk in ranks:  # the windows are all-clear again after a completed run (what the next run relies on)
         assert all(c is CLEAR for c in rk.inbox) and all(c is CLEAR for g in rk.gather for c in g)
@@ -112,7 +124,7 @@ def test_bfs_exchange_has_no_hazard_under_random_interleavings(world):
 
 
 def test_single_gather_buffer_would_be_a_hazard():
-    """Without the epoch-parity double buffer a fast peer delivers level L+1 into the area this rank still merges."""
+    """Without the epoch-parity double buffer a fast peer delivers level L+1 into the area this rank still reads."""
     rng = random.Random(7)
     with pytest.raises(AssertionError):
         for _ in range(500):
