@@ -685,25 +685,35 @@ def run_distributed(args, rank, world, local_rank):
              "exchange_kind": runner.exchange_kind()}
         if check_single and scale <= 26:
             # rank 0 rebuilds the whole graph and runs the single-GPU ess_bfs on the same sources
-            equal = True
+            equal, failure = True, None
             fulls = []
             with torch.cuda.stream(stream):
                 for s in timed[:4]:
                     runner.bfs(s)
-                    fulls.append(runner.gather_depth() if rank == 0 else runner.gather_depth() * 0)
+                    full = runner.gather_depth()
+                    if rank == 0:
+                        fulls.append(full)
+                    del full
+            stream.synchronize()
             if rank == 0:
-                with torch.cuda.stream(stream):
-                    csr = gg.rmat_csr(scale, args.edge_factor, device=dev)
-                    c1 = ess.Context(local_rank, stream=stream)
-                    g1 = ess.Graph(csr)
-                    for s, full in zip(timed[:4], fulls):
-                        d1, _ = ess.bfs(c1, g1, s, lb="merge_path", direction="optimized")
-                        equal = equal and bool(torch.equal(d1, full))
-                    del g1, csr, d1
+                try:  # whatever happens here, rank 0 must reach the collective below (the others wait in it)
+                    with torch.cuda.stream(stream):
+                        csr = gg.rmat_csr(scale, args.edge_factor, device=dev)
+                        stream.synchronize()
+                        c1 = ess.Context(local_rank, stream=stream)
+                        g1 = ess.Graph(csr)
+                        for s, full in zip(timed[:4], fulls):
+                            d1, _ = ess.bfs(c1, g1, s, lb="merge_path", direction="optimized")
+                            equal = equal and bool(torch.equal(d1, full))
+                        del g1, csr, d1
+                except Exception as e:
+                    equal, failure = False, repr(e)[:300]
             del fulls
             torch.cuda.empty_cache()
             r["equal_single_gpu_bfs"] = bool(all_sum(0 if equal else 1) == 0)
             r["single_gpu_sources_compared"] = len(timed[:4])
+            if failure:
+                r["single_gpu_check_error"] = failure
         if not args.no_e2e and check_single:
             csr = runner.csr
             h_off, h_col = csr.offsets.cpu().pin_memory(), csr.indices.cpu().pin_memory()
@@ -819,7 +829,10 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that dies must not leave the others in a collective for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=240))
         try:
             return run_distributed(args, rank, world, local_rank)
         finally:

@@ -179,6 +179,10 @@ int ess_graph_build_pull_hints(ess_graph_t h, const int32_t* d_degree_of_id) {
   ESS_TRY
   if (!h || !h->has_csc) return ess::fail("ess_graph_build_pull_hints: graph has no CSC view");
   if (h->n <= 0 || h->m <= 0) return 0;
+  // The hint kernels run on the legacy default stream, which does NOT wait for non-blocking streams (torch's, or a
+  // context's own): the caller's CSR arrays may still be being written (H2D copy, generator kernels) on one of
+  // those. Graph creation is set-up code, so wait for the whole device before reading them.
+  error::throw_if_exception(cudaDeviceSynchronize(), "ess_graph_build_pull_hints: pending work failed");
   h->hint_head.resize(std::size_t(h->n));
   h->hint_isolated.resize((std::size_t(h->n) + 31) / 32 + 1);
   if (h->offset_bits == 64) {
@@ -203,6 +207,8 @@ int ess_transpose_csr(int64_t n, int64_t m, int offset_bits, const void* d_row_o
                       const int32_t* d_column_indices, const float* d_values, void* d_out_offsets,
                       int32_t* d_out_indices, float* d_out_values) {
   ESS_TRY
+  // set-up code on the legacy default stream: wait for producers of the input arrays on non-blocking streams
+  error::throw_if_exception(cudaDeviceSynchronize(), "ess_transpose_csr: pending work failed");
   if (offset_bits == 64)
     graph::build::detail::transpose_on_device<int32_t, int64_t, float>(
         int32_t(n), int64_t(m), (const int64_t*)d_row_offsets, d_column_indices, d_values, d_out_indices,

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_ncu_summarise_reproduces_committed_traffic(tmp_path):
-    csv = os.path.join(ROOT, "profiles", "r01e_launches_bfs_kron24.csv")
+    csv = os.path.join(ROOT, "profiles", "r02e_launches_bfs_kron26.csv")
     out_json = str(tmp_path / "traffic.json")
     out_txt = str(tmp_path / "shares.txt")
     run = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summarise.py"), csv, "--shares", out_txt,
