@@ -3,3 +3,4 @@
 #include <cstdio>
 #include <gunrock/cuda/context.hxx>
 #include <gunrock/cuda/launch.hxx>
+#include <gunrock/cuda/launch_box.hxx>

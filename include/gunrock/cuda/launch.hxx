@@ -4,8 +4,9 @@
  *
  * The reference picks launch parameters at compile time from an SM_TARGET macro through launch_box_t
  * (include/gunrock/cuda/launch_box.hxx:194-335, sm flags end at sm_86: include/gunrock/cuda/sm.hxx:23-39).
- * This build targets exactly one architecture (sm_100a, 148 SMs), so the "launch box" collapses to a
- * persistent-grid rule: operators launch min(needed CTAs, SMs x resident CTAs) and grid-stride.
+ * This build targets exactly one architecture (sm_100a), so inside the operators the "launch box" collapses to a
+ * persistent-grid rule: min(needed CTAs, SMs x resident CTAs of that kernel from the occupancy API), grid-stride.
+ * gcuda::launch_box (cuda/launch_box.hxx) keeps the reference's type for user kernels that name one.
  */
 #pragma once
 
@@ -15,7 +16,6 @@
 namespace gunrock {
 namespace gcuda {
 
-enum sm_flag_t : unsigned { fallback = ~0u, sm_100 = 1u << 16 };
 
 namespace thread {
 namespace global {
