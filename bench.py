@@ -797,12 +797,13 @@ def run_distributed(args, rank, world, local_rank):
         sec = out.setdefault("other_configs", {})
         try:
             weak_scale = 24 + max(world.bit_length() - 1, 0)
-            if weak_scale != args.scale and time.time() - T0 < args.extras_budget_s:
+            # the skip decisions must be the same on every rank (measure() is collective): agree on the elapsed time
+            if weak_scale != args.scale and all_max(time.time() - T0) < args.extras_budget_s:
                 w = measure(weak_scale, min(K, 8), min(W, 3))
                 sec["weak_scaling"] = {k: w[k] for k in ("scale", "n", "m", "gteps", "ms", "steps",
                                                          "certificate_violations", "nvlink_bytes")}
                 parity_ok = parity_ok and w["certificate_violations"] == 0
-            if world == 8 and args.scale != 28 and time.time() - T0 < args.extras_budget_s:
+            if world == 8 and args.scale != 28 and all_max(time.time() - T0) < args.extras_budget_s:
                 c5 = measure(28, min(K, 6), 2, sssp_steps=2)
                 sec["config5_scale28"] = {k: c5.get(k) for k in ("scale", "n", "m", "gteps", "ms", "steps", "sssp",
                                                                  "certificate_violations", "nvlink_bytes")}

@@ -105,35 +105,67 @@ __global__ void __launch_bounds__(256)
 
 /// head[v] = in-neighbour of v with the largest degree (ties: first in the list), head_edge[v] = that in-edge;
 /// head[v] = -1 for vertices without in-edges, and -2 - u for vertices whose single in-edge comes from u. `degree_offsets` is the offsets array degrees are read from
-/// (the CSR when present, so "degree" is the out-degree of the in-neighbour). One warp per vertex.
+/// (the CSR when present, so "degree" is the out-degree of the in-neighbour). One lane per vertex, warp for long lists.
 template <typename vertex_t, typename edge_t>
 __global__ void __launch_bounds__(256)
     pull_hints_kernel(vertex_t n, const edge_t* __restrict__ in_offsets, const vertex_t* __restrict__ in_indices,
                       const edge_t* __restrict__ degree_offsets, const vertex_t* __restrict__ degree_of,
                       vertex_t* __restrict__ head, edge_t* __restrict__ head_edge) {
+  // One lane per vertex: lists of up to 16 in-edges (most vertices of a power-law graph) are scanned by their own
+  // lane, longer ones by the whole warp in coalesced strides (a warp per vertex, the first version, spent 34 ms at
+  // scale-26 mostly on degree-1/2 vertices with one busy lane). Arg-max rule in both paths: largest degree, earliest edge.
   const unsigned lane = threadIdx.x & 31;
   const std::size_t warps = (std::size_t(gridDim.x) * blockDim.x) >> 5;
-  for (std::size_t v = (std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; v < std::size_t(n); v += warps) {
-    const edge_t b = in_offsets[v], e = in_offsets[v + 1];
+  auto degree = [&](vertex_t u) -> long long {
+    return degree_of ? (long long)degree_of[u] : (long long)(degree_offsets[u + 1] - degree_offsets[u]);
+  };
+  for (std::size_t base = ((std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * 32; base < std::size_t(n);
+       base += warps * 32) {
+    const std::size_t v = base + lane;
+    edge_t b = 0, e = 0;
+    if (v < std::size_t(n)) {
+      b = in_offsets[v];
+      e = in_offsets[v + 1];
+    }
     long long best_deg = -1;
     edge_t best_edge = e;
-    for (edge_t k = b + lane; k < e; k += 32) {
-      const vertex_t u = in_indices[k];
-      const long long d = degree_of ? (long long)degree_of[u] : (long long)(degree_offsets[u + 1] - degree_offsets[u]);
-      if (d > best_deg) {  // strict: keeps the earliest edge of this lane on ties
-        best_deg = d;
-        best_edge = k;
+    const bool is_long = e - b > edge_t(16);
+    if (!is_long)
+      for (edge_t k = b; k < e; ++k) {
+        const long long d = degree(in_indices[k]);
+        if (d > best_deg) {  // strict: keeps the earliest edge on ties
+          best_deg = d;
+          best_edge = k;
+        }
+      }
+    unsigned long_lanes = __ballot_sync(0xffffffffu, is_long);
+    while (long_lanes) {
+      const int owner = __ffs(long_lanes) - 1;
+      long_lanes &= long_lanes - 1;
+      const edge_t ob = __shfl_sync(0xffffffffu, b, owner), oe = __shfl_sync(0xffffffffu, e, owner);
+      long long bd = -1;
+      edge_t be = oe;
+      for (edge_t k = ob + edge_t(lane); k < oe; k += 32) {
+        const long long d = degree(in_indices[k]);
+        if (d > bd) {
+          bd = d;
+          be = k;
+        }
+      }
+      for (int s = 16; s > 0; s >>= 1) {  // (degree desc, edge asc) arg-max across the warp
+        const long long od = __shfl_xor_sync(0xffffffffu, bd, s);
+        const edge_t oe2 = __shfl_xor_sync(0xffffffffu, be, s);
+        if (od > bd || (od == bd && oe2 < be)) {
+          bd = od;
+          be = oe2;
+        }
+      }
+      if (int(lane) == owner) {
+        best_deg = bd;
+        best_edge = be;
       }
     }
-    for (int s = 16; s > 0; s >>= 1) {  // (degree desc, edge asc) arg-max across the warp
-      const long long od = __shfl_xor_sync(0xffffffffu, best_deg, s);
-      const edge_t oe = __shfl_xor_sync(0xffffffffu, best_edge, s);
-      if (od > best_deg || (od == best_deg && oe < best_edge)) {
-        best_deg = od;
-        best_edge = oe;
-      }
-    }
-    if (lane == 0) {
+    if (v < std::size_t(n)) {
       // >= 0: the hint; -1: no in-edges; <= -2: the ONLY in-neighbour is -2 - head[v] (nothing to walk on a miss)
       vertex_t h = vertex_t(-1);
       if (best_deg >= 0) {
