@@ -30,6 +30,7 @@ int fail(const char* message, int code = 999);
 /// ess_tune("dist_peer_exchange"): 1 = the partitioned BFS exchanges its bitmaps with its own peer-memory
 /// kernels when the IPC window could be mapped (default), 0 = NCCL collectives.
 int& dist_peer_exchange();
+int& dist_peer_timeout_ms();  ///< ess_tune("dist_peer_timeout_ms"): how long a rank waits for a peer's level data (4000)
 int& dist_trace();  ///< ess_tune("dist_trace"): per-phase event timing of ess_dist_bfs on stderr (rank 0)
 
 }  // namespace ess

@@ -32,6 +32,10 @@ int& dist_trace() {
   static int on = 0;
   return on;
 }
+int& dist_peer_timeout_ms() {
+  static int ms = 4000;
+  return ms;
+}
 }  // namespace ess
 
 extern "C" {
@@ -101,6 +105,11 @@ int ess_tune(const char* knob, int value) {
   }
   if (k == "dist_peer_exchange") {
     ess::dist_peer_exchange() = value;
+    return 0;
+  }
+  if (k == "dist_peer_timeout_ms") {
+    if (value <= 0) return ess::fail("ess_tune: dist_peer_timeout_ms must be positive");
+    ess::dist_peer_timeout_ms() = value;
     return 0;
   }
   return ess::fail("ess_tune: unknown knob");

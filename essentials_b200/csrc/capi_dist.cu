@@ -501,31 +501,27 @@ static __global__ void __launch_bounds__(256)
   raise_flags_when_grid_done(peers, world, rank, flag_off, epoch, done);
 }
 
-/// all_gather: this rank's row (row_words words) lands in row `rank` of every peer's gather area.
-static __global__ void __launch_bounds__(256)
-    peer_broadcast_kernel(const unsigned* __restrict__ row, peers_t peers, int world, int rank, unsigned row_words,
-                          std::size_t gather_off, std::size_t flag_off, unsigned epoch, unsigned* done) {
-  const std::size_t pairs = row_words / 2, total = pairs * world;
-  const uint2* in = reinterpret_cast<const uint2*>(row);
-  for (std::size_t i = std::size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += std::size_t(gridDim.x) * blockDim.x) {
-    const int p = int(i / pairs);
-    const std::size_t k = i - std::size_t(p) * pairs;
-    const uint2 v = in[k];
-    if (v.x | v.y)  // receivers zero the area while merging it (merge_gathered_kernel, consume)
-      reinterpret_cast<uint2*>(peers.base[p] + gather_off + std::size_t(rank) * row_words)[k] = v;
-  }
-  raise_flags_when_grid_done(peers, world, rank, flag_off, epoch, done);
+static unsigned long long peer_timeout_ns() {
+  return (unsigned long long)(ess::dist_peer_timeout_ms() > 0 ? ess::dist_peer_timeout_ms() : 4000) * 1000000ull;
 }
 
-/// Stream-side wait: returns once every peer's flag reached `epoch`; gives up after ~4 s (a dead peer must not
-/// hang the box) and reports through *timed_out (mapped host memory).
-static __global__ void peer_wait_kernel(const unsigned* flags, int world, unsigned epoch, unsigned* timed_out) {
+/// Wall-clock nanoseconds (independent of the SM clock, unlike clock64).
+static __device__ __forceinline__ unsigned long long wall_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+/// Stream-side wait: returns once every peer's flag reached `epoch`; gives up after `timeout_ns` (ess_tune
+/// "dist_peer_timeout_ms", default 4 s: a dead peer must not hang the box) and reports through *timed_out (mapped
+/// host memory) — the host then poisons the handle, see ess_dist_s::poisoned.
+static __global__ void peer_wait_kernel(const unsigned* flags, int world, unsigned epoch, unsigned* timed_out,
+                                        unsigned long long timeout_ns) {
   if (threadIdx.x >= unsigned(world)) return;
   const volatile unsigned* flag = flags + threadIdx.x;
-  const long long start = clock64();
+  const unsigned long long start = wall_ns();
   while (int(*flag - epoch) < 0) {
-    if (clock64() - start > 8000000000LL) {
+    if (wall_ns() - start > timeout_ns) {
       *timed_out = 1u + threadIdx.x;
       break;
     }
@@ -573,12 +569,12 @@ static __global__ void __launch_bounds__(256)
 /// a PCIe write instead of cudaMemcpyAsync(D2H) + cudaStreamSynchronize.
 static __global__ void peer_wait_publish_kernel(const unsigned* flags, int world, unsigned epoch, unsigned* timed_out,
                                                 unsigned* cnt_area, volatile long long* host_counts,
-                                                unsigned long long sequence) {
+                                                unsigned long long sequence, unsigned long long timeout_ns) {
   if (threadIdx.x < unsigned(world)) {
     const volatile unsigned* flag = flags + threadIdx.x;
-    const long long start = clock64();
+    const unsigned long long start = wall_ns();
     while (int(*flag - epoch) < 0) {
-      if (clock64() - start > 8000000000LL) {
+      if (wall_ns() - start > timeout_ns) {
         *timed_out = 1u + threadIdx.x;
         break;
       }
@@ -692,6 +688,10 @@ struct ess_dist_s {
   bool sssp_peer_tried = false, sssp_peer_ready = false;
   unsigned* done_counter = nullptr;  // device word of raise_flags_when_grid_done
   unsigned* timed_out = nullptr;     // pinned, mapped
+  // A peer that missed a level leaves this rank's windows, epochs and counters in an unknown state (the consuming
+  // kernels ran on partial data, later flags may still arrive): every later call on the handle fails fast instead of
+  // computing on it or waiting on ranks that have moved on. Destroy the handle on every rank and create a new one.
+  bool poisoned = false;
   std::shared_ptr<gunrock::gcuda::partition_t> partition;  // NCCL bound to the operator-API partition descriptor
   ~ess_dist_s() {
     for (int p = 0; p < world && p < max_peers; ++p)
@@ -829,7 +829,7 @@ int ess_dist_create(ess_context_t ctx, ess_graph_t g, int rank, int world, int64
       }
       void* mapped = nullptr;
       ok = cudaIpcOpenMemHandle(&mapped, all[p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-      d->peers.base[p] = static_cast<unsigned*>(mapped);
+      d->peers.base[p] = ok ? static_cast<unsigned*>(mapped) : nullptr;
     }
     cudaGetLastError();  // a failed mapping only means the NCCL exchange is used
     // every rank must take the same path: agree on the outcome
@@ -947,6 +947,7 @@ int ess_dist_destroy(ess_dist_t d) {
 int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_info* info) {
   ESS_TRY
   if (!d) return ess::fail("ess_dist_bfs: null handle");
+  if (d->poisoned) return ess::fail("ess_dist_bfs: an earlier peer exchange on this handle timed out; destroy and recreate it");
   if (source < 0 || source >= d->n_global) return ess::fail("ess_dist_bfs: source out of range");
   if (!(alpha > 0)) alpha = 14.f;
   if (!(beta > 0)) beta = 24.f;
@@ -1039,7 +1040,7 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
       if (peer) {  // candidate slices go straight into the owners' inboxes over NVLink
         peer_scatter_kernel<<<gcuda::persistent_grid(*c, (std::size_t(words) / 2 + 255) / 256, 4), 256, 0, stream>>>(
             d->candidate_bits.data(), d->peers, world, rank, wper, d->inbox_off, d->flag_off[0], epoch, d->done_counter);
-        peer_wait_kernel<<<1, 32, 0, stream>>>(d->window + d->flag_off[0], world, epoch, d->timed_out);
+        peer_wait_kernel<<<1, 32, 0, stream>>>(d->window + d->flag_off[0], world, epoch, d->timed_out, peer_timeout_ns());
         c->profiler().launches_total += 2;
       } else {
         nccl_check(api.GroupStart(), "group");
@@ -1081,7 +1082,7 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
       mark(3);
       const unsigned long long sequence = ++d->level_sequence;
       peer_wait_publish_kernel<<<1, 32, 0, stream>>>(d->window + d->flag_off[1], world, epoch, d->timed_out,
-                                                     d->window + cnts, d->level_counts, sequence);
+                                                     d->window + cnts, d->level_counts, sequence, peer_timeout_ns());
       c->profiler().launches_total += 2;
       mark(4);
       mark(5);
@@ -1114,7 +1115,10 @@ int ess_dist_bfs(ess_dist_t d, int64_t source, float alpha, float beta, ess_run_
     if (peer && *d->timed_out) {
       const unsigned who = *d->timed_out - 1;
       *d->timed_out = 0;
-      throw error::exception_t("ess_dist_bfs: peer " + std::to_string(who) + " did not deliver its level data");
+      d->poisoned = true;
+      throw error::exception_t("ess_dist_bfs: peer " + std::to_string(who) + " did not deliver its level data within " +
+                               std::to_string(peer_timeout_ns() / 1000000ull) +
+                               " ms (ess_tune dist_peer_timeout_ms); the handle is unusable from here on");
     }
     prev_n_f = n_f;
     n_f = 0;
@@ -1192,7 +1196,11 @@ static void setup_sssp_window(ess_dist_t d) {
   c->synchronize();
   for (int p = 0; p < world && ok; ++p) {
     void* mapped = d->replica_window;
-    if (p != rank) ok = cudaIpcOpenMemHandle(&mapped, all[p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    if (p != rank) {
+      mapped = nullptr;
+      ok = cudaIpcOpenMemHandle(&mapped, all[p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      if (!ok) mapped = nullptr;  // the destructor closes every non-null peer mapping: never our own window
+    }
     d->replicas.value[p] = static_cast<const float*>(mapped);
     d->replicas.dirty[p] = ok ? reinterpret_cast<const unsigned*>(static_cast<const float*>(mapped) + n) : nullptr;
   }
@@ -1209,6 +1217,7 @@ static void setup_sssp_window(ess_dist_t d) {
 int ess_dist_sssp(ess_dist_t d, int64_t source, ess_run_info* info) {
   ESS_TRY
   if (!d) return ess::fail("ess_dist_sssp: null handle");
+  if (d->poisoned) return ess::fail("ess_dist_sssp: an earlier peer exchange on this handle timed out; destroy and recreate it");
   if (source < 0 || source >= d->n_global) return ess::fail("ess_dist_sssp: source out of range");
   auto* c = d->ctx->single();
   auto stream = c->stream();
@@ -1248,7 +1257,7 @@ int ess_dist_sssp(ess_dist_t d, int64_t source, ess_run_info* info) {
       cudaMemsetAsync(dirty, 0, dirty_words * sizeof(unsigned), stream);  // peers finished reading: all_reduce below
       ESS_WITH_GRAPH(g, G, { partition_relax(d->ctx, G, active, my_count, dist_local, replica, dirty); })
       peer_signal_kernel<<<1, 32, 0, stream>>>(d->peers, world, rank, d->flag_off[0], epoch);
-      peer_wait_kernel<<<1, 32, 0, stream>>>(d->window + d->flag_off[0], world, epoch, d->timed_out);
+      peer_wait_kernel<<<1, 32, 0, stream>>>(d->window + d->flag_off[0], world, epoch, d->timed_out, peer_timeout_ns());
       cudaMemsetAsync(counts, 0, 2 * sizeof(long long), stream);
       const unsigned grid = gcuda::persistent_grid(*c, per / 1024, 8);
       auto* cnt = reinterpret_cast<b200::counter_t*>(counts);
@@ -1272,7 +1281,10 @@ int ess_dist_sssp(ess_dist_t d, int64_t source, ess_run_info* info) {
     if (peer && *d->timed_out) {
       const unsigned who = *d->timed_out - 1;
       *d->timed_out = 0;
-      throw error::exception_t("ess_dist_sssp: peer " + std::to_string(who) + " did not finish its relaxation round");
+      d->poisoned = true;
+      throw error::exception_t("ess_dist_sssp: peer " + std::to_string(who) + " did not finish its relaxation round within " +
+                               std::to_string(peer_timeout_ns() / 1000000ull) +
+                               " ms (ess_tune dist_peer_timeout_ms); the handle is unusable from here on");
     }
     my_count = d->counts_host[0];
     total = d->counts_host[2];

@@ -249,7 +249,10 @@ ESS_API int ess_dist_depth_local(ess_dist_t d, int32_t** d_depth_local, int64_t*
 /* How ess_dist_bfs moves its bitmaps between ranks: 1 = the library's own peer-memory kernels (every rank maps
  * the others' exchange window with cudaIpcOpenMemHandle at ess_dist_create; a sender stores its slices straight
  * into the receivers' windows over NVLink and raises an epoch flag, the receiver's stream waits on the flags),
- * 0 = NCCL send/recv + all_gather (mapping failed, or ess_tune("dist_peer_exchange", 0)). */
+ * 0 = NCCL send/recv + all_gather (mapping failed, or ess_tune("dist_peer_exchange", 0)).
+ * A rank whose stream waited longer than ess_tune("dist_peer_timeout_ms") (default 4000, wall clock) for a peer's
+ * level data returns an error and marks the handle unusable: later ess_dist_bfs / ess_dist_sssp calls on it fail
+ * immediately; destroy the handle on every rank and create a new one. */
 ESS_API int ess_dist_exchange_kind(ess_dist_t d, int* kind);
 ESS_API int ess_dist_copy_depth(ess_dist_t d, int32_t* d_out); /* owned depth slice -> caller buffer, on the stream */
 

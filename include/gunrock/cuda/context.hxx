@@ -229,6 +229,7 @@ class standard_context_t {
   standard_context_t(const standard_context_t&) = delete;
   standard_context_t& operator=(const standard_context_t&) = delete;
   ~standard_context_t() {
+    memory::device_pool_t::instance().unregister_stream(_stream);
     cudaEventDestroy(_event);
     if (_owns_stream) cudaStreamDestroy(_stream);
   }
@@ -272,6 +273,7 @@ class standard_context_t {
 
  private:
   void init() {
+    memory::device_pool_t::instance().register_stream(_stream);  // the pool's release() respects work queued here
     error::throw_if_exception(cudaEventCreateWithFlags(&_event, cudaEventDisableTiming), "event create");
     error::throw_if_exception(cudaGetDeviceProperties(&_props, _ordinal), "device properties");
     _timer.set_stream(_stream);

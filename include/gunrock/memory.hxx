@@ -26,8 +26,13 @@ enum memory_space_t { device, host };
  * buffers (two frontiers, work offsets, bitmaps, per-vertex state); cudaMalloc/cudaFree cost 0.1-1 ms each
  * and cudaFree synchronises the device, which is more than a whole BFS on B200. Blocks are returned to a
  * per-(device, rounded size) free list instead and handed out again on the next run, so after the first
- * run of a given shape no call reaches the driver. Safe because every operator synchronises its stream
- * before returning: a block is only released by host code after the GPU is done with it.
+ * run of a given shape no call reaches the driver.
+ * Stream safety (what cudaFree's implicit device synchronisation used to give): every stream the library launches on
+ * is registered (standard_context_t does it). release() asks each registered stream of the block's device whether it
+ * still has work queued (cudaStreamQuery, ~1 us; the usual answer after an operator's end-of-level synchronisation is
+ * "idle") and only for a busy stream records an event that travels with the cached block; acquire() waits for those
+ * events on the host before it hands the block out, so a block can never reach a second user — another context,
+ * another stream, a legacy-stream memcpy — while kernels enqueued before its release may still touch it.
  * The cache is intentionally never destroyed at exit (the CUDA runtime may already be gone).
  */
 class device_pool_t {
@@ -48,11 +53,15 @@ class device_pool_t {
       for (auto it = cached.lower_bound({dev, rounded}); it != cached.end() && it->first.first == dev; ++it) {
         if (it->first.second > 2 * rounded + (std::size_t(4) << 20)) break;
         if (it->second.empty()) continue;
-        void* p = it->second.back();
+        block_t blk = it->second.back();
         it->second.pop_back();
         cached_bytes -= it->first.second;
-        live[p] = it->first;
-        return p;
+        live[blk.p] = it->first;
+        for (cudaEvent_t ev : blk.pending) {  // work that was still queued when the block was released
+          cudaEventSynchronize(ev);
+          spare_events.push_back(ev);
+        }
+        return blk.p;
       }
     }
     void* p = nullptr;
@@ -75,9 +84,49 @@ class device_pool_t {
       cudaFree(p);
       return;
     }
-    cached[it->second].push_back(p);
+    block_t blk;
+    blk.p = p;
+    for (auto& st : streams) {
+      if (st.dev != it->second.first) continue;
+      const cudaError_t state = cudaStreamQuery(st.stream);
+      if (state == cudaSuccess) continue;  // idle: nothing queued can touch the block
+      cudaGetLastError();                  // (cudaErrorNotReady is not an error)
+      if (state != cudaErrorNotReady) continue;  // a caller-owned stream that no longer exists
+      cudaEvent_t ev = nullptr;
+      if (!spare_events.empty()) {
+        ev = spare_events.back();
+        spare_events.pop_back();
+      } else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamSynchronize(st.stream);  // no event to be had: wait here instead
+        continue;
+      }
+      cudaEventRecord(ev, st.stream);
+      blk.pending.push_back(ev);
+    }
+    cached[it->second].push_back(std::move(blk));
     cached_bytes += it->second.second;
     live.erase(it);
+  }
+  /// Streams whose queued work release() must respect (see the class comment). The device is the current one.
+  void register_stream(cudaStream_t stream) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& st : streams)
+      if (st.dev == dev && st.stream == stream) {
+        ++st.users;
+        return;
+      }
+    streams.push_back({dev, stream, 1});
+  }
+  void unregister_stream(cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(mu);
+    for (std::size_t i = 0; i < streams.size(); ++i)
+      if (streams[i].stream == stream) {
+        if (--streams[i].users == 0) streams.erase(streams.begin() + i);
+        break;
+      }
   }
   /// Return every cached (unused) block to the driver.
   void trim() {
@@ -86,7 +135,10 @@ class device_pool_t {
     cudaGetDevice(&cur);
     for (auto& kv : cached) {
       cudaSetDevice(kv.first.first);
-      for (void* p : kv.second) cudaFree(p);
+      for (auto& blk : kv.second) {
+        cudaFree(blk.p);  // synchronises the device: the pending events have fired
+        for (cudaEvent_t ev : blk.pending) spare_events.push_back(ev);
+      }
       kv.second.clear();
     }
     cudaSetDevice(cur);
@@ -104,8 +156,19 @@ class device_pool_t {
     const std::size_t grain = std::size_t(2) << 20;
     return (b + grain - 1) / grain * grain;
   }
+  struct block_t {
+    void* p = nullptr;
+    std::vector<cudaEvent_t> pending;
+  };
   std::mutex mu;
-  std::map<std::pair<int, std::size_t>, std::vector<void*>> cached;
+  std::map<std::pair<int, std::size_t>, std::vector<block_t>> cached;
+  struct stream_ref_t {
+    int dev;
+    cudaStream_t stream;
+    int users;
+  };
+  std::vector<stream_ref_t> streams;
+  std::vector<cudaEvent_t> spare_events;
   std::unordered_map<void*, std::pair<int, std::size_t>> live;
   std::size_t cached_bytes = 0;
 };

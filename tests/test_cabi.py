@@ -62,3 +62,13 @@ def test_product_never_imports_the_oracle():
         for f in files:
             assert "oracle" not in open(os.path.join(base, f)).read().replace("the oracle", "").replace(
                 "Jacobi oracle", "").replace("/oracle stream", ""), f
+
+
+def test_tune_knobs_are_validated_on_the_host():
+    """ess_tune is host-only state: unknown knobs and a non-positive peer timeout are refused with a message."""
+    ess.tune("dist_peer_timeout_ms", 2500)
+    ess.tune("dist_peer_timeout_ms", 4000)
+    with pytest.raises(ess.EssentialsError, match="positive"):
+        ess.tune("dist_peer_timeout_ms", 0)
+    with pytest.raises(ess.EssentialsError, match="unknown knob"):
+        ess.tune("no_such_knob", 1)
