@@ -596,7 +596,7 @@ def side_runs(args, ctx, dev, out, peak_gbs):
         pr_csr = gg.rmat_csr(25, args.edge_factor, symmetric=False, weights="ones", device=dev)
         pr_graph = ess.Graph(pr_csr, csc=ess.transpose(pr_csr))
         p_pull, i_pull = ess.pagerank(ctx, pr_graph, pull=True)
-        p_push, i_push = ess.pagerank(ctx, pr_graph, lb="merge_path")
+        p_push, i_push = ess.pagerank(ctx, pr_graph, lb="merge_path", pull=False)
         rel = ((p_pull.double() - p_push.double()).abs().sum() / p_pull.double().sum()).item()
         it = max(i_pull["iterations"], 1)
         per_iter_bytes = pr_csr.m * 12 + pr_csr.n * (2 * 4 + 9 * 4)

@@ -287,11 +287,20 @@ def sssp_delta(ctx: Context, g: Graph, source: int, delta: float = 0.0, out=None
 
 
 def pagerank(ctx: Context, g: Graph, alpha: float = 0.85, tol: float = 1e-6, max_iterations: int = 1000,
-             lb: str = "block_mapped", pull: bool = False, out=None):
-    """gunrock::pr::run (reference include/gunrock/algorithms/pr.hxx:183-216). Returns (p[float32], info)."""
+             lb: str = "block_mapped", pull: bool | None = None, out=None):
+    """gunrock::pr::run (reference include/gunrock/algorithms/pr.hxx:183-216). Returns (p[float32], info).
+
+    `pull=None` (default) gathers over the in-edge view whenever the graph has one (a CSC, or a symmetric CSR): every
+    vertex sums its contributions in one fixed order, and the ranks agree with the reference's CPU PageRank to 1e-6
+    per element — this is the parity path. `pull=False` is the reference's formulation, an advance that scatters
+    `atomic::add` over the out-edges with balancer `lb`; float additions then arrive in whatever order the hardware
+    schedules them, so individual ranks can differ by up to ~1e-4 relative from run to run (1e-6 in L1), exactly as
+    the reference's GPU PageRank does. Without an in-edge view the default is the scatter."""
     import torch
     p = _out(g.n, torch.float32, g.csr.indices) if out is None else out
     info = RunInfo()
+    if pull is None:
+        pull = bool(g.has_csc)
     _check(lib().ess_pagerank(ctx.handle, g.handle, alpha, tol, max_iterations, _p(p), LOAD_BALANCE[lb], int(pull),
                               byref(info)), "ess_pagerank")
     return p, info.as_dict()

@@ -37,6 +37,6 @@ if args.pr_scale:
     csr = gg.rmat_csr(args.pr_scale, symmetric=False, weights="ones", device="cuda")
     g = ess.Graph(csr, csc=ess.transpose(csr))
     want, ref_ms = oracle.ref_gpu_run("pr", csr, 0.85, 1e-6)
-    got, info = ess.pagerank(ctx, g, lb="merge_path")
+    got, info = ess.pagerank(ctx, g, lb="merge_path", pull=False)
     rel = ((got.double() - want.double()).abs().sum() / want.double().sum()).item()
     print(f"PR scale-{args.pr_scale}: reference {ref_ms:.1f} ms | ours merge_path {info['enact_ms']:.1f} ms ({info['iterations']} iters) rel-L1 {rel:.2e}", flush=True)
