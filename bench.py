@@ -410,17 +410,18 @@ def run_single(args, rank, local_rank):
     # ---- e2e: host buffers in, host buffer out, graph handle (incl. hints) rebuilt, every step -------------
     last_depth = None
     if not args.no_e2e:
-        h_off = csr.offsets.cpu().pin_memory()
-        h_col = csr.indices.cpu().pin_memory()
+        h_csr = csr.pinned()  # the caller's graph: host arrays in page-locked memory
         h_depth = torch.empty(n, dtype=torch.int32).pin_memory()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         with torch.cuda.stream(stream):
+            ess.Graph.from_host(ctx, h_csr).close()  # untimed: the device blocks of the handle come from the driver once
+            torch.cuda.synchronize()
             f0.record(stream)
             for s in timed:
-                csr.offsets.copy_(h_off, non_blocking=True)
-                csr.indices.copy_(h_col, non_blocking=True)
-                g = ess.Graph(csr)  # ess_graph_create: views + bottom-up hints + isolated bitmap
+                # ess_graph_create_from_host: H2D of offsets + indices into device arrays the handle owns, graph views,
+                # bottom-up hints and isolated-vertex bitmap (built chunk by chunk under the copy)
+                g = ess.Graph.from_host(ctx, h_csr)
                 one_bfs(s, g)
                 h_depth.copy_(depth, non_blocking=True)
                 stream.synchronize()
@@ -429,13 +430,19 @@ def run_single(args, rank, local_rank):
         torch.cuda.synchronize()
         ems = f0.elapsed_time(f1)
         out["e2e"] = {"value": edges / (ems * 1e-3) / 1e9, "unit": "GTEPS",
-                      "h2d_bytes_per_step": int(h_off.numel() * h_off.element_size() + h_col.numel() * 4),
+                      "h2d_bytes_per_step": int(h_csr.nbytes()),
                       "d2h_bytes_per_step": int(n * 4), "ms_per_step": ems / K,
-                      "what": "per step: CSR offsets+indices H2D from pinned memory, ess_graph_create (graph views, "
-                              "bottom-up hints, isolated-vertex bitmap: nothing is reused between steps), ess_bfs, "
-                              "depth D2H, ess_graph_destroy"}
+                      "what": "per step, from host arrays: ess_graph_create_from_host (CSR offsets+indices H2D from "
+                              "pinned memory in chunks, graph views, bottom-up hints and isolated-vertex bitmap built "
+                              "under the copy; nothing is reused between steps), ess_bfs, depth D2H, "
+                              "ess_graph_destroy"}
         last_depth = h_depth.numpy().copy()
-        del h_off, h_col
+        del h_csr
+        with torch.cuda.stream(stream):  # the host-array path must give the depths of the resident graph
+            one_bfs(timed[-1])
+        stream.synchronize()
+        out["e2e"]["depths_equal_resident_graph"] = bool(torch.equal(depth.cpu(), h_depth))
+        parity_ok = parity_ok and out["e2e"]["depths_equal_resident_graph"]
 
     # ---- CPU baseline: the reference's bfs_cpu, one source of the same graph --------------------------------
     if not args.no_cpu:

@@ -56,6 +56,8 @@ _SIGNATURES = {
     "ess_tune": (c_int, [c_char_p, c_int]),
     "ess_profile_enable": (c_int, [c_void_p, c_int]),
     "ess_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    "ess_graph_create_from_host": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                           POINTER(c_void_p)]),
     "ess_graph_create": (c_int, [c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                  c_void_p, POINTER(c_void_p)]),
     "ess_graph_destroy": (c_int, [c_void_p]),
@@ -219,6 +221,37 @@ class Graph:
                                       _p(csc.values) if csc is not None else None, byref(h)), "ess_graph_create")
         self.handle = h
         self.has_csc = sym or csc is not None
+        self.device = csr.indices.device
+
+    @classmethod
+    def from_host(cls, ctx: "Context", csr, symmetric: bool | None = None):
+        """ess_graph_create_from_host: `csr` holds HOST tensors (pinned memory lets the copy overlap); the handle owns
+        the device copies, and the bottom-up hints are built chunk by chunk while the column indices are still crossing
+        PCIe. Mirrors the reference drivers' host csr_t -> device vectors -> from_csr sequence
+        (examples/algorithms/bfs/bfs.cu:25-66)."""
+        import torch
+        for t in (csr.offsets, csr.indices, csr.values):
+            if t is not None and t.is_cuda:
+                raise EssentialsError("Graph.from_host takes host tensors; use Graph(csr) for device arrays")
+            if t is not None and not t.is_contiguous():
+                raise EssentialsError("Graph.from_host needs contiguous arrays")
+        if csr.indices.dtype != torch.int32 or (csr.values is not None and csr.values.dtype != torch.float32):
+            raise EssentialsError("Graph.from_host: column indices are int32 and values float32")
+        self = cls.__new__(cls)
+        self.csr, self.csc = csr, None
+        self.n, self.m = int(csr.offsets.numel() - 1), int(csr.indices.numel())
+        self.offset_bits = 64 if csr.offsets.element_size() == 8 else 32
+        sym = bool(csr.symmetric) if symmetric is None else bool(symmetric)
+        self.handle = None
+        h = c_void_p()
+        with torch.cuda.device(ctx.device):
+            _check(lib().ess_graph_create_from_host(ctx.handle, self.n, self.m, self.offset_bits, _p(csr.offsets),
+                                                    _p(csr.indices), _p(csr.values), int(sym), byref(h)),
+                   "ess_graph_create_from_host")
+        self.handle = h
+        self.has_csc = sym
+        self.device = torch.device("cuda", ctx.device)
+        return self
 
     def build_pull_hints(self, degree_of_id=None):
         """graph::build::pull_hints; degree_of_id (int32 per global id) is required for partitions."""
@@ -236,16 +269,16 @@ class Graph:
             pass
 
 
-def _out(n, dtype, like):
+def _out(n, dtype, g):
     import torch
-    return torch.empty(n, dtype=dtype, device=like.device)
+    return torch.empty(n, dtype=dtype, device=g.device)
 
 
 def bfs(ctx: Context, g: Graph, source: int, lb: str = "block_mapped", direction: str = "forward", out=None,
         alpha: float = 0.0, beta: float = 0.0):
     """gunrock::bfs::run (reference include/gunrock/algorithms/bfs.hxx:151-176). Returns (depth[int32], info)."""
     import torch
-    depth = _out(g.n, torch.int32, g.csr.indices) if out is None else out
+    depth = _out(g.n, torch.int32, g) if out is None else out
     info = RunInfo()
     _check(lib().ess_bfs(ctx.handle, g.handle, int(source), _p(depth), LOAD_BALANCE[lb], DIRECTION[direction],
                          alpha, beta, byref(info)), "ess_bfs")
@@ -255,7 +288,7 @@ def bfs(ctx: Context, g: Graph, source: int, lb: str = "block_mapped", direction
 def sssp(ctx: Context, g: Graph, source: int, lb: str = "block_mapped", out=None):
     """gunrock::sssp::run (reference include/gunrock/algorithms/sssp.hxx:155-185). Returns (dist[float32], info)."""
     import torch
-    dist = _out(g.n, torch.float32, g.csr.indices) if out is None else out
+    dist = _out(g.n, torch.float32, g) if out is None else out
     info = RunInfo()
     _check(lib().ess_sssp(ctx.handle, g.handle, int(source), _p(dist), LOAD_BALANCE[lb], byref(info)), "ess_sssp")
     return dist, info.as_dict()
@@ -264,7 +297,7 @@ def sssp(ctx: Context, g: Graph, source: int, lb: str = "block_mapped", out=None
 def sssp_near_far(ctx: Context, g: Graph, source: int, delta: float = 0.0, out=None):
     """SSSP through operators::advance::execute_near_far (near/far ordering in one persistent kernel)."""
     import torch
-    dist = _out(g.n, torch.float32, g.csr.indices) if out is None else out
+    dist = _out(g.n, torch.float32, g) if out is None else out
     info = RunInfo()
     _check(lib().ess_sssp_near_far(ctx.handle, g.handle, int(source), _p(dist), float(delta), byref(info)),
            "ess_sssp_near_far")
@@ -276,7 +309,7 @@ def sssp_near_far(ctx: Context, g: Graph, source: int, delta: float = 0.0, out=N
 def sssp_delta(ctx: Context, g: Graph, source: int, delta: float = 0.0, out=None):
     """SSSP through gunrock::sssp::run_delta (dense active set + delta thresholds; for low-diameter graphs)."""
     import torch
-    dist = _out(g.n, torch.float32, g.csr.indices) if out is None else out
+    dist = _out(g.n, torch.float32, g) if out is None else out
     info = RunInfo()
     _check(lib().ess_sssp_delta(ctx.handle, g.handle, int(source), _p(dist), float(delta), byref(info)),
            "ess_sssp_delta")
@@ -297,7 +330,7 @@ def pagerank(ctx: Context, g: Graph, alpha: float = 0.85, tol: float = 1e-6, max
     schedules them, so individual ranks can differ by up to ~1e-4 relative from run to run (1e-6 in L1), exactly as
     the reference's GPU PageRank does. Without an in-edge view the default is the scatter."""
     import torch
-    p = _out(g.n, torch.float32, g.csr.indices) if out is None else out
+    p = _out(g.n, torch.float32, g) if out is None else out
     info = RunInfo()
     if pull is None:
         pull = bool(g.has_csc)
@@ -310,7 +343,7 @@ def ppr(ctx: Context, g: Graph, seed: int, alpha: float = 0.15, epsilon: float =
         out=None):
     """gunrock::ppr::run (reference include/gunrock/algorithms/ppr.hxx:150-179)."""
     import torch
-    p = _out(g.n, torch.float32, g.csr.indices) if out is None else out
+    p = _out(g.n, torch.float32, g) if out is None else out
     info = RunInfo()
     _check(lib().ess_ppr(ctx.handle, g.handle, int(seed), alpha, epsilon, _p(p), LOAD_BALANCE[lb], byref(info)),
            "ess_ppr")
@@ -320,7 +353,7 @@ def ppr(ctx: Context, g: Graph, seed: int, alpha: float = 0.15, epsilon: float =
 def kcore(ctx: Context, g: Graph, lb: str = "block_mapped", out=None):
     """gunrock::kcore::run (reference include/gunrock/algorithms/kcore.hxx:202-222)."""
     import torch
-    k = _out(g.n, torch.int32, g.csr.indices) if out is None else out
+    k = _out(g.n, torch.int32, g) if out is None else out
     info = RunInfo()
     _check(lib().ess_kcore(ctx.handle, g.handle, _p(k), LOAD_BALANCE[lb], byref(info)), "ess_kcore")
     return k, info.as_dict()
@@ -329,7 +362,7 @@ def kcore(ctx: Context, g: Graph, lb: str = "block_mapped", out=None):
 def color(ctx: Context, g: Graph, out=None):
     """gunrock::color::run (reference include/gunrock/algorithms/color.hxx:155-180)."""
     import torch
-    c = _out(g.n, torch.int32, g.csr.indices) if out is None else out
+    c = _out(g.n, torch.int32, g) if out is None else out
     info = RunInfo()
     _check(lib().ess_color(ctx.handle, g.handle, _p(c), byref(info)), "ess_color")
     return c, info.as_dict()

@@ -51,6 +51,10 @@ struct ess_graph_s {
   gunrock::memory::device_array_t<int32_t> hint_edge32;
   gunrock::memory::device_array_t<int64_t> hint_edge64;
   gunrock::memory::device_array_t<unsigned> hint_isolated;
+  // device copies owned by the handle (ess_graph_create_from_host); empty when the caller owns the arrays
+  gunrock::memory::device_array_t<unsigned char> own_offsets;
+  gunrock::memory::device_array_t<int32_t> own_indices;
+  gunrock::memory::device_array_t<float> own_values;
 };
 
 #define ESS_TRY try {

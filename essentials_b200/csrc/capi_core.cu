@@ -3,6 +3,8 @@
  * @brief C ABI: errors, contexts, graph handles, transpose, random stream, frontier conversions.
  */
 #include "capi_common.hxx"
+#include <algorithm>
+#include <memory>
 #include <gunrock/algorithms/generate/random.hxx>
 #include <gunrock/algorithms/sssp.hxx>
 
@@ -35,6 +37,12 @@ int& dist_trace() {
 int& dist_peer_timeout_ms() {
   static int ms = 4000;
   return ms;
+}
+/// ess_tune("host_chunk_edges"): column indices per H2D chunk of ess_graph_create_from_host (256 MB by default;
+/// tests shrink it so that small graphs cross many chunk boundaries).
+int& host_chunk_edges() {
+  static int edges = 64 << 20;
+  return edges;
 }
 }  // namespace ess
 
@@ -105,6 +113,11 @@ int ess_tune(const char* knob, int value) {
   }
   if (k == "dist_peer_exchange") {
     ess::dist_peer_exchange() = value;
+    return 0;
+  }
+  if (k == "host_chunk_edges") {
+    if (value <= 0) return ess::fail("ess_tune: host_chunk_edges must be positive");
+    ess::host_chunk_edges() = value;
     return 0;
   }
   if (k == "dist_peer_timeout_ms") {
@@ -180,6 +193,133 @@ int ess_graph_create(int64_t n, int64_t m, int offset_bits, const void* d_row_of
     }
   }
   *out = h;
+  return 0;
+  ESS_CATCH
+}
+
+}  // extern "C"
+
+namespace {
+/// A private copy stream and the events that order the context's stream behind its copies.
+struct copy_lane_t {
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> events;
+  copy_lane_t() { error::throw_if_exception(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "copy stream"); }
+  ~copy_lane_t() {
+    for (auto e : events) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+  /// Everything enqueued on `follower` after this call waits for the copies enqueued so far.
+  void publish_to(cudaStream_t follower) {
+    cudaEvent_t e = nullptr;
+    error::throw_if_exception(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "copy event");
+    events.push_back(e);
+    error::throw_if_exception(cudaEventRecord(e, stream), "copy event record");
+    error::throw_if_exception(cudaStreamWaitEvent(follower, e, 0), "copy event wait");
+  }
+};
+
+/// ess_graph_create_from_host for one offset width. The offsets go first (degrees and the isolated-vertex bitmap need
+/// nothing else), then the column indices in chunks of `chunk_edges`; after each chunk the context's stream builds the
+/// bottom-up hints of the vertices whose lists have fully arrived, so at scale-26 the ~30 ms hint build runs under the
+/// ~155 ms PCIe copy instead of after it.
+template <typename edge_t>
+void create_from_host(ess_context_t ctx, ess_graph_s* h, const void* h_row_offsets, const int32_t* h_column_indices,
+                      const float* h_values, bool symmetric) {
+  auto* c = ctx->single();
+  cudaStream_t work = c->stream();
+  const std::size_t n = std::size_t(h->n), m = std::size_t(h->m);
+  const edge_t* ho = static_cast<const edge_t*>(h_row_offsets);
+  error::throw_if_exception(ho[0] != edge_t(0) || std::size_t(ho[n]) != m,
+                            "ess_graph_create_from_host: row_offsets[0] must be 0 and row_offsets[n] must be m");
+  h->own_offsets.resize((n + 1) * sizeof(edge_t));
+  h->own_indices.resize(m);
+  if (h_values) h->own_values.resize(m);
+  edge_t* d_off = reinterpret_cast<edge_t*>(h->own_offsets.data());
+  int32_t* d_idx = h->own_indices.data();
+  float* d_val = h_values ? h->own_values.data() : nullptr;
+
+  copy_lane_t lane;
+  error::throw_if_exception(cudaMemcpyAsync(d_off, ho, (n + 1) * sizeof(edge_t), cudaMemcpyHostToDevice, lane.stream),
+                            "ess_graph_create_from_host: offsets copy");
+  lane.publish_to(work);
+  const bool hints = symmetric && n > 0 && m > 0;
+  memory::device_array_t<int32_t> degree;
+  edge_t* hint_edge = nullptr;
+  if (hints) {
+    h->hint_head.resize(n);
+    h->hint_isolated.resize((n + 31) / 32 + 1);
+    if constexpr (sizeof(edge_t) == 8) {
+      h->hint_edge64.resize(n);
+      hint_edge = h->hint_edge64.data();
+    } else {
+      h->hint_edge32.resize(n);
+      hint_edge = h->hint_edge32.data();
+    }
+    degree.resize(n);
+    graph::build::detail::degrees_kernel<<<2048, 256, 0, work>>>(int32_t(n), d_off, degree.data());
+    graph::build::detail::isolated_bitmap_kernel<<<2048, 256, 0, work>>>(int32_t(n), d_off, h->hint_isolated.data());
+  }
+  const std::size_t chunk_edges = std::size_t(ess::host_chunk_edges());  // 256 MB of column indices per copy
+  std::size_t built = 0;                                  // vertices whose hints are enqueued
+  for (std::size_t e0 = 0; e0 < m; e0 += chunk_edges) {
+    const std::size_t e1 = std::min(m, e0 + chunk_edges);
+    error::throw_if_exception(cudaMemcpyAsync(d_idx + e0, h_column_indices + e0, (e1 - e0) * sizeof(int32_t),
+                                              cudaMemcpyHostToDevice, lane.stream),
+                              "ess_graph_create_from_host: indices copy");
+    if (!hints) continue;
+    lane.publish_to(work);
+    // vertices [built, arrived) end at or before e1: the last offset that is <= e1 bounds them (host-side search)
+    const std::size_t arrived = std::size_t(std::upper_bound(ho, ho + n + 1, edge_t(e1)) - ho) - 1;
+    graph::build::pull_hints_range(int32_t(built), int32_t(arrived), d_off, d_idx, degree.data(), h->hint_head.data(),
+                                   hint_edge, work);
+    built = std::max(built, arrived);
+  }
+  if (d_val)
+    error::throw_if_exception(cudaMemcpyAsync(d_val, h_values, m * sizeof(float), cudaMemcpyHostToDevice, lane.stream),
+                              "ess_graph_create_from_host: values copy");
+  error::throw_if_exception(cudaStreamSynchronize(lane.stream), "ess_graph_create_from_host: copy");
+  error::throw_if_exception(cudaStreamSynchronize(work), "ess_graph_create_from_host: hint build");
+  error::check_last("ess_graph_create_from_host");
+
+  auto G = graph::build::from_csr_and_csc<int32_t, edge_t, float>(int32_t(n), edge_t(m), d_off, d_idx, d_val,
+                                                                  symmetric ? d_off : nullptr,
+                                                                  symmetric ? d_idx : nullptr,
+                                                                  symmetric ? d_val : nullptr);
+  if (hints) {
+    graph::graph_csc_t<int32_t, edge_t, float>& csc = G;
+    csc.set_pull_hints(h->hint_head.data(), hint_edge, h->hint_isolated.data());
+  }
+  if constexpr (sizeof(edge_t) == 8)
+    h->g64 = G;
+  else
+    h->g32 = G;
+}
+}  // namespace
+
+extern "C" {
+
+int ess_graph_create_from_host(ess_context_t ctx, int64_t n, int64_t m, int offset_bits, const void* h_row_offsets,
+                               const int32_t* h_column_indices, const float* h_values, int symmetric,
+                               ess_graph_t* out) {
+  ESS_TRY
+  if (!ctx || !out || !h_row_offsets || (m > 0 && !h_column_indices))
+    return ess::fail("ess_graph_create_from_host: null argument");
+  if (offset_bits != 32 && offset_bits != 64)
+    return ess::fail("ess_graph_create_from_host: offset_bits must be 32 or 64");
+  if (n < 0 || n > 2147483647LL) return ess::fail("ess_graph_create_from_host: vertex ids are int32");
+  if (m < 0 || (offset_bits == 32 && m > 2147483647LL))
+    return ess::fail("ess_graph_create_from_host: m needs 64-bit offsets");
+  std::unique_ptr<ess_graph_s> h(new ess_graph_s);
+  h->offset_bits = offset_bits;
+  h->n = n;
+  h->m = m;
+  h->has_csc = symmetric != 0;
+  if (offset_bits == 64)
+    create_from_host<int64_t>(ctx, h.get(), h_row_offsets, h_column_indices, h_values, symmetric != 0);
+  else
+    create_from_host<int32_t>(ctx, h.get(), h_row_offsets, h_column_indices, h_values, symmetric != 0);
+  *out = h.release();
   return 0;
   ESS_CATCH
 }

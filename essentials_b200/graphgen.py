@@ -110,6 +110,11 @@ class CSR:
         return CSR(self.n, self.m, self.offsets.to(device), self.indices.to(device),
                    None if self.values is None else self.values.to(device), self.name, self.symmetric)
 
+    def pinned(self) -> "CSR":
+        """Host copy in page-locked memory (what Graph.from_host overlaps its transfer from)."""
+        pin = lambda t: None if t is None else t.cpu().contiguous().pin_memory()
+        return CSR(self.n, self.m, pin(self.offsets), pin(self.indices), pin(self.values), self.name, self.symmetric)
+
     def host(self):
         """numpy views for the oracle (offsets widened to int64)."""
         off = self.offsets.cpu().numpy().astype("int64")

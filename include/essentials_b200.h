@@ -91,6 +91,15 @@ ESS_API int ess_graph_create(int64_t n, int64_t m, int offset_bits, const void* 
                      const int32_t* d_column_indices, const float* d_values, int symmetric,
                      const void* d_column_offsets, const int32_t* d_row_indices, const float* d_csc_values,
                      ess_graph_t* out);
+/* The same graph from HOST arrays — what the reference's drivers do around from_csr: load a host csr_t, assign it to
+ * device vectors (format conversion + thrust copies, examples/algorithms/bfs/bfs.cu:44-66), build the views. The handle
+ * owns the device copies. The transfer is pipelined on a private copy stream: offsets first, then the column indices
+ * in 256 MB chunks, and the bottom-up hints of the vertices whose lists have arrived are built on the context's stream
+ * while later chunks are still crossing PCIe (pinned host memory overlaps; pageable memory works, unoverlapped).
+ * symmetric = 1: the CSC view aliases the copies and hints are built; 0: CSR only. Returns with the graph complete. */
+ESS_API int ess_graph_create_from_host(ess_context_t ctx, int64_t n, int64_t m, int offset_bits,
+                                       const void* h_row_offsets, const int32_t* h_column_indices,
+                                       const float* h_values, int symmetric, ess_graph_t* out);
 ESS_API int ess_graph_destroy(ess_graph_t g);
 /* (Re)builds the bottom-up hints of graph::build::pull_hints (include/gunrock/graph/build.hxx; no reference
  * counterpart): per vertex, its highest-degree in-neighbour. d_degree_of_id: degree of every id that may appear

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256)
 /// (the CSR when present, so "degree" is the out-degree of the in-neighbour). One lane per vertex, warp for long lists.
 template <typename vertex_t, typename edge_t>
 __global__ void __launch_bounds__(256)
-    pull_hints_kernel(vertex_t n, const edge_t* __restrict__ in_offsets, const vertex_t* __restrict__ in_indices,
+    pull_hints_kernel(vertex_t first, vertex_t n, const edge_t* __restrict__ in_offsets,
+                      const vertex_t* __restrict__ in_indices,
                       const edge_t* __restrict__ degree_offsets, const vertex_t* __restrict__ degree_of,
                       vertex_t* __restrict__ head, edge_t* __restrict__ head_edge) {
   // One lane per vertex: lists of up to 16 in-edges (most vertices of a power-law graph) are scanned by their own
@@ -119,8 +120,9 @@ __global__ void __launch_bounds__(256)
   auto degree = [&](vertex_t u) -> long long {
     return degree_of ? (long long)degree_of[u] : (long long)(degree_offsets[u + 1] - degree_offsets[u]);
   };
-  for (std::size_t base = ((std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * 32; base < std::size_t(n);
-       base += warps * 32) {
+  // vertices [first, n): the streamed build (pull_hints_range) calls this once per arrived chunk of the indices
+  for (std::size_t base = std::size_t(first) + ((std::size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * 32;
+       base < std::size_t(n); base += warps * 32) {
     const std::size_t v = base + lane;
     edge_t b = 0, e = 0;
     if (v < std::size_t(n)) {
@@ -298,12 +300,27 @@ void pull_hints(graph_type& G, typename graph_type::vertex_type* head, typename 
     degree_of = degree_scratch.data();
   }
   if (n > 0)
-    detail::pull_hints_kernel<<<2048, 256, 0, stream>>>(n, c.get_column_offsets(), c.get_row_indices(), degree_offsets,
-                                                        degree_of, head, head_edge);
+    detail::pull_hints_kernel<<<2048, 256, 0, stream>>>(decltype(n)(0), n, c.get_column_offsets(), c.get_row_indices(),
+                                                        degree_offsets, degree_of, head, head_edge);
   if (n > 0 && isolated_words)
     detail::isolated_bitmap_kernel<<<2048, 256, 0, stream>>>(n, c.get_column_offsets(), isolated_words);
   error::throw_if_exception(cudaStreamSynchronize(stream), "pull_hints");
   c.set_pull_hints(head, head_edge, isolated_words);
+}
+
+/**
+ * @brief Hints of the vertices [first, last) only, enqueued on `stream` without synchronising: the building block of a
+ * graph that is still arriving from the host (ess_graph_create_from_host copies the column indices in chunks and calls
+ * this for the vertices whose lists are complete, so the hint build hides behind the PCIe copy). `degree_of` must hold
+ * the degree of every id that can appear in the lists.
+ */
+template <typename vertex_t, typename edge_t>
+void pull_hints_range(vertex_t first, vertex_t last, const edge_t* in_offsets, const vertex_t* in_indices,
+                      const vertex_t* degree_of, vertex_t* head, edge_t* head_edge, cudaStream_t stream) {
+  if (last <= first) return;
+  const std::size_t ctas = (std::size_t(last - first) + 255) / 256;
+  detail::pull_hints_kernel<<<unsigned(ctas < 2048 ? ctas : 2048), 256, 0, stream>>>(
+      first, last, in_offsets, in_indices, in_offsets, degree_of, head, head_edge);
 }
 
 /// Wrap pre-built CSR and CSC arrays (no computation): used by the C ABI when the caller owns both.

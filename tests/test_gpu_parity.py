@@ -75,6 +75,58 @@ def test_bfs_int64_offsets(ctx, golden):
             assert np.array_equal(depth.cpu().numpy(), golden["rmat_s10"][f"bfs_{s}"])
 
 
+@pytest.mark.parametrize("wide", [False, True])
+def test_graph_from_host_arrays(ctx, s16, wide):
+    """ess_graph_create_from_host (the reference drivers' host csr_t -> device vectors -> from_csr,
+    examples/algorithms/bfs/bfs.cu:25-66): chunked H2D on a copy stream with the bottom-up hints built per arrived
+    chunk. Chunks of 4096 edges make the scale-16 graph cross ~500 chunk boundaries (vertices whose lists straddle a
+    boundary, hubs that span several chunks); depths and distances must equal the device-array graph, pinned or
+    pageable host memory, 32- or 64-bit offsets, and the counters must show the hinted bottom-up levels."""
+    csr, g, (off, col, _) = s16
+    src = gg.pick_sources(csr, 2)
+    ess.tune("host_chunk_edges", 4096)
+    try:
+        for pinned in (True, False):
+            host = csr.pinned() if pinned else csr.to("cpu")
+            if wide:
+                host = gg.CSR(host.n, host.m, host.offsets.long(), host.indices, host.values, host.name, host.symmetric)
+                if pinned:
+                    host = host.pinned()
+            gh = ess.Graph.from_host(ctx, host)
+            assert gh.has_csc and gh.offset_bits == (64 if wide else 32)
+            for s in src:
+                for lb, direction in (("merge_path", "optimized"), ("block_mapped", "forward")):
+                    want, i0 = ess.bfs(ctx, g, s, lb=lb, direction=direction)
+                    got, i1 = ess.bfs(ctx, gh, s, lb=lb, direction=direction)
+                    assert torch.equal(want, got), (pinned, wide, s, lb, direction)
+                    assert np.array_equal(got.cpu().numpy(), oracle.bfs(off, col, s))
+                    if direction == "optimized" and not wide:
+                        assert i1["pull_steps"] == i0["pull_steps"] >= 1
+                        for k in ("pull_vertices", "pull_misses", "pull_found"):  # same hints -> same bottom-up work
+                            assert i1[k] == i0[k], (k, i0, i1)
+            gh.close()
+        weighted = gg.rmat_csr(12, weights="hash", device="cpu")  # the values array travels last
+        gw, gd = ess.Graph.from_host(ctx, weighted.pinned()), ess.Graph(weighted.to("cuda"))
+        for s in gg.pick_sources(weighted, 2):
+            assert torch.equal(ess.sssp(ctx, gw, s)[0], ess.sssp(ctx, gd, s)[0])
+        gw.close()
+    finally:
+        ess.tune("host_chunk_edges", 64 << 20)
+    with pytest.raises(ess.EssentialsError):
+        ess.Graph.from_host(ctx, csr)  # device tensors belong to Graph(csr)
+    bad = csr.to("cpu")
+    bad = gg.CSR(bad.n, bad.m, bad.offsets.clone(), bad.indices, None, "", True)
+    bad.offsets[-1] += 1
+    with pytest.raises(ess.EssentialsError, match="row_offsets"):
+        ess.Graph.from_host(ctx, bad)
+    directed = ess.Graph.from_host(ctx, gg.rmat_csr(8, symmetric=False, device="cpu"), symmetric=False)
+    assert not directed.has_csc
+    d, _ = ess.bfs(ctx, directed, 0)
+    assert int(d[0]) == 0
+    with pytest.raises(ess.EssentialsError):
+        ess.bfs(ctx, directed, 0, direction="optimized")
+
+
 def test_bfs_isolated_source_and_errors(ctx, s16):
     csr, g, (off, col, _) = s16
     iso = int(torch.nonzero(csr.degrees() == 0)[0])
