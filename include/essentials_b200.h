@@ -126,7 +126,7 @@ ESS_API int ess_sssp(ess_context_t ctx, ess_graph_t g, int32_t source, float* d_
 /* Same distances as ess_sssp through operators::advance::execute_near_far (include/gunrock/framework/operators/
  * advance/near_far.cuh): near/far priority ordering — the method the reference's load_balance_t::bucketing
  * enumerator cites (configs.hxx:35) but leaves empty (advance/bucketing.hxx:31-36) — inside one persistent
- * kernel. delta: bucket width (<= 0: mean edge weight). info->iterations = near levels; reserved[0] levels,
+ * kernel. delta: bucket width (<= 0: 64 x mean edge weight / mean degree). info->iterations = near levels; reserved[0] levels,
  * [1] far-pile splits, [2] relaxations. */
 ESS_API int ess_sssp_near_far(ess_context_t ctx, ess_graph_t g, int32_t source, float* d_dist, float delta,
                               ess_run_info* info);

@@ -13,7 +13,8 @@
  * `near_far = true` (additive): the same relaxation operator driven by operators::advance::execute_near_far —
  * Davidson et al.'s near/far ordering inside one persistent kernel (advance/near_far.cuh) — for high-diameter
  * graphs where the level-per-launch loop above is latency- and rework-bound. `delta` is the bucket width
- * (<= 0: the mean edge weight). Same distances, bit for bit.
+ * (<= 0: 64 x mean edge weight / mean degree — the mean weight on a degree-64 graph, narrower buckets for denser
+ * ones, wider for sparse ones such as grids and road networks). Same distances, bit for bit.
  *
  * `run_delta` (additive): the same relaxation with a DENSE active set and a distance threshold, for low-diameter
  * graphs with big frontiers (Kronecker/RMAT). Per round one streaming pass over (dist, expanded-at) picks the
