@@ -72,3 +72,19 @@ def test_tune_knobs_are_validated_on_the_host():
         ess.tune("dist_peer_timeout_ms", 0)
     with pytest.raises(ess.EssentialsError, match="unknown knob"):
         ess.tune("no_such_knob", 1)
+
+
+def test_graph_from_host_validates_arrays_before_touching_the_device():
+    """Graph.from_host refuses non-contiguous arrays and wrong element types on the host side (no context needed)."""
+    import torch
+    from essentials_b200 import graphgen
+    g = graphgen.rmat_csr(6)
+    wrong_ids = graphgen.CSR(g.n, g.m, g.offsets, g.indices.long(), None, "", True)
+    with pytest.raises(ess.EssentialsError, match="int32"):
+        ess.Graph.from_host(None, wrong_ids)
+    strided = graphgen.CSR(g.n, g.m, g.offsets, torch.stack([g.indices, g.indices], 1)[:, 0], None, "", True)
+    with pytest.raises(ess.EssentialsError, match="contiguous"):
+        ess.Graph.from_host(None, strided)
+    wrong_w = graphgen.CSR(g.n, g.m, g.offsets, g.indices, torch.ones(g.m, dtype=torch.float64), "", True)
+    with pytest.raises(ess.EssentialsError, match="float32"):
+        ess.Graph.from_host(None, wrong_w)
