@@ -16,9 +16,9 @@ SURVEY.md §8d) summed over the steps / time. Rank 0 prints ONE JSON line.
                reference's own bfs_cpu; at N > 1 every rank certifies its rows against the all-gathered depths (and
                at N = 2 they are also compared with a single-GPU ess_bfs on rank 0). A mismatch sets parity_ok false
                and the exit code to 3.
-  e2e          the same K sources through the public host API with HOST buffers: every step copies the CSR arrays
-               from pinned host memory, builds the graph handle (incl. the bottom-up hints), runs BFS, copies the
-               depth array back and destroys the handle.
+  e2e          the same K sources through the public host API with HOST buffers: every step hands the CSR arrays in
+               pinned host memory to ess_graph_create_from_host (H2D copy + graph handle incl. the bottom-up hints,
+               built under the copy), runs BFS, copies the depth array back and destroys the handle.
   roofline     dominant kernel class of an instrumented repeat of the K steps (CUDA events around every launch):
                algorithmic bytes / kernel time vs the measured HBM peak in MEASURED_PEAKS.json.
   cpu_baseline the reference's own bfs_cpu (oracle/_ref, 1 thread) on one source of the same graph, rank 0, N=1.
