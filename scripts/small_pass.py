@@ -1,7 +1,8 @@
-"""A small pass over the traversal kernels for compute-sanitizer (memcheck): graph built from host arrays in many small
-chunks, BFS through every balancer and both directions, SSSP (frontier, near-far, dense delta), k-core, filters.
-Results are checked against the oracle so that a silent fault cannot pass.
-    compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitize_small.py"""
+"""A small pass over the traversal kernels in one process (a few seconds on a GPU): graph built from pageable host arrays
+in 1024-edge chunks, BFS through every balancer and both directions, SSSP (frontier, near-far, dense delta), k-core,
+filters; every result is checked against the oracle. Written as the workload for `compute-sanitizer --tool memcheck`
+(closed on this pool, so the recorded run is plain).
+    python scripts/small_pass.py"""
 import numpy as np
 import torch
 
@@ -30,4 +31,4 @@ assert np.array_equal(k.cpu().numpy(), oracle.kcore(off, col))
 items = torch.arange(0, csr.n, dtype=torch.int32, device="cuda")
 for alg in ("predicated", "compact", "bypass", "remove"):
     ess.filter_probe(ctx, g, items, alg=alg)
-print("SANITIZE_SMALL_OK")
+print("SMALL_PASS_OK")
